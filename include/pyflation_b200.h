@@ -1,0 +1,153 @@
+/* pyflation_b200.h -- C ABI of the B200-native first-order hot path of ihuston/pyflation.
+ *
+ * The library replaces, for CanonicalBackground / CanonicalFirstOrder models, what the
+ * reference does in pure Python/NumPy inside
+ *     pyflation/rk4.py:58-138          rkdriver_tsix   (the time loop, NaN prefill, IC scatter)
+ *     pyflation/rk4.py:27-55           rk4stepks       (one classical RK4 step)
+ *     pyflation/cosmomodels.py:551-571 CanonicalBackground.derivs
+ *     pyflation/cosmomodels.py:625-675 CanonicalFirstOrder.derivs
+ *     pyflation/cmpotentials.py:16-1144  the 18 potential functions (U, dU, d2U)
+ *     pyflation/analysis/adiabatic.py:153-285  Pr / scaled_Pr (pf_pr_spectrum)
+ * The reference has no FFI of its own (a Python callable `derivs` is passed to the solver),
+ * so the binding a maintainer adds is the ctypes stub shown in INTEGRATION.md; the host-side
+ * mirror of the reference's modules that does this lives in pyflation_b200/{rk4,cosmomodels}.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `*_dev` pointers are device memory of the CURRENT CUDA
+ *     device, `*_host` pointers are host memory.  The caller owns every buffer; the library
+ *     allocates nothing that outlives a call and keeps no state except a thread-local error
+ *     string.  `stream` is a cudaStream_t passed as void* (NULL = default stream).  All
+ *     launches are asynchronous on `stream`.
+ *   - complex128 buffers are arrays of (re, im) double pairs, NumPy layout.
+ *   - trajectory layout is the reference's: yresult[t][var][k], k innermost (rk4.py:95-100),
+ *     var order  phi_0, phi'_0, ..., phi_{nf-1}, phi'_{nf-1}, H, dphi_00, dphi'_00, dphi_01, ...
+ *     (cosmomodels.py:613-623);  nvar = 2 nf^2 + 2 nf + 1.
+ *   - return value: 0 = OK; < 0 = argument error (PF_E_*), mirrors rk4.SimRunError /
+ *     cosmomodels.ModelError on the Python side; > 0 = cudaError_t.  pf_last_error() gives text.
+ */
+#ifndef PYFLATION_B200_H
+#define PYFLATION_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PF_ABI_VERSION 1
+#define PF_MAX_NFIELDS 8          /* compiled instantiations: nf = 1..8 */
+#define PF_MAX_PARAMS 8
+
+/* potential ids, in the order of pyflation/cmpotentials.py */
+enum pf_potential {
+    PF_MSQPHISQ = 0,          /* cmpotentials.py:16    params: mass */
+    PF_LAMBDAPHI4 = 1,        /* :74    lambda */
+    PF_LINDE = 2,             /* :131   mass, lambda */
+    PF_HYBRID2AND4 = 3,       /* :201   mass, lambda */
+    PF_PHI2OVER3 = 4,         /* :271   sigma */
+    PF_MSQPHISQ_WITHV0 = 5,   /* :328   mass, V0 */
+    PF_STEP_POTENTIAL = 6,    /* :391   mass, c, d, phi_s */
+    PF_BUMP_POTENTIAL = 7,    /* :468   mass, c, d, phi_b */
+    PF_RESONANCE = 8,         /* :545   mass, c, d */
+    PF_BUMP_NOTHIRDDERIV = 9, /* :621   mass, c, d, phi_b */
+    PF_HYBRIDQUADRATIC = 10,  /* :696   m1, m2 */
+    PF_RIDGE_TWOFIELD = 11,   /* :744   g, m, V0 */
+    PF_NFLATION = 12,         /* :791   mass  (nfields comes from pf_model.nfields) */
+    PF_QUARTICTWOFIELD = 13,  /* :848   m1, m2, l1, l2 */
+    PF_HYBRIDQUARTIC = 14,    /* :896   lambda, v, mu, phi_c */
+    PF_INFLECTION = 15,       /* :963   lambda, g, r, m */
+    PF_HILLTOPAXION = 16,     /* :1026  Lambda, f, m */
+    PF_PRODUCTEXPONENTIAL = 17, /* :1088 lambda, V_0 */
+    PF_NUM_POTENTIALS = 18
+};
+
+enum pf_error {
+    PF_OK = 0,
+    PF_E_ARG = -1,            /* null pointer / negative size / bad window */
+    PF_E_POTENTIAL = -2,      /* unknown potential id, or nfields not valid for it */
+    PF_E_NFIELDS = -3,        /* nfields outside 1..PF_MAX_NFIELDS */
+    PF_E_STEP = -4,           /* h is NaN or zero   (rk4.py:63 "Need to specify h.") */
+    PF_E_START = -5           /* start index outside the step range (rk4.py:74) */
+};
+
+/* What cosmomodels.CosmologicalModel.__init__ resolves from (potential_func, pot_params,
+ * nfields) (cosmomodels.py:135-154) plus CanonicalFirstOrder's ainit (:592-596). */
+typedef struct pf_model {
+    int32_t potential_id;
+    int32_t nfields;
+    double params[PF_MAX_PARAMS];     /* order given per potential above */
+    double ainit;                     /* a(t) = ainit * exp(t); unused by pf_bg_run */
+} pf_model;
+
+/* flags written by pf_fo_run into *flags_dev (bitwise OR) */
+#define PF_FLAG_BG_MISMATCH 1   /* a column's ystart background rows are not on column 0's trajectory */
+
+int pf_version(void);
+const char *pf_last_error(void);
+
+/* ---- potential table (seam 2: cosmomodels.py:136-139 resolves potential_func by name) ---- */
+int pf_potential_id(const char *name);             /* -1 if unknown */
+const char *pf_potential_name(int id);             /* NULL if unknown */
+int pf_potential_nfields(int id);                  /* 1, 2, or 0 = any (nflation) */
+int pf_potential_nparams(int id);
+const char *pf_potential_param_name(int id, int i);
+double pf_potential_param_default(int id, int i);
+
+/* Evaluate (U, dU, d2U) on the device at n points; y_dev is [n][2nf+1] real background
+ * vectors.  Replaces cmpotentials.<name>(y, params)[0:3].  d2U_dev may be NULL. */
+int pf_potential_eval(const pf_model *m, int64_t n, const double *y_dev, double *U_dev,
+                      double *dU_dev, double *d2U_dev, void *stream);
+
+/* ---- sizes ---- */
+int64_t pf_number_of_steps(double simtstart, double tend, double h);  /* rk4.py:73 */
+int64_t pf_nvar(int nfields);                      /* 2 nf^2 + 2 nf + 1 */
+int64_t pf_rec_doubles(int nfields);               /* doubles per step record (below) */
+
+/* ---- K1: background RK4 (replaces rkdriver_tsix + CanonicalBackground.derivs) ----
+ * Integrates the real background y = (phi_i, phi'_i, H) from row n0 (state y0_host) to row
+ * T-1 with step h.  bg_dev[T][2nf+1]: rows < n0 are NaN, row n0 = y0.  stagey_dev (may be
+ * NULL) [T][4][2nf+1] receives the four RK4 stage arguments of every step n -> n+1. */
+int pf_bg_run(const pf_model *m, int64_t T, double h, int64_t n0, const double *y0_host,
+              double *bg_dev, double *stagey_dev, void *stream);
+
+/* ---- K1b: per-step records consumed by pf_fo_run ----
+ * rec_dev[T][pf_rec_doubles(nf)]:  for each RK4 stage s=0..3 of the step n -> n+1:
+ * A = U/H^2,  R = 1/(a H),  C[i][l] = (V_il + phi'_i V_l + V_i phi'_l + phi'_i phi'_l U)/H^2
+ * (cosmomodels.py:663-674), a = ainit exp(t_stage), t_stage = simtstart + n h (+ h/2, + h/2,
+ * + h) (rk4.py:27-55,116-118); then the bg row n (2nf+1 doubles); padded to an even length.
+ * Rows n < n0 are NaN. */
+int pf_stage_table(const pf_model *m, int64_t T, double simtstart, double h, int64_t n0,
+                   const double *bg_dev, const double *stagey_dev, double *rec_dev,
+                   void *stream);
+
+/* ---- K2/K3: first-order perturbation RK4 over a batch of k modes ----
+ * Replaces rkdriver_tsix + rk4stepks + CanonicalFirstOrder.derivs for rows [t0, t1).
+ *   k_dev[nk], tsix_dev[nk] (start row per mode), ystart_dev c128 [nvar][nk] (row tsix_k of
+ *   column k is exactly ystart[:,k]; rows before it are NaN+NaNj; rows after it are RK4).
+ *   state_dev c128 [2 nf^2][nk]: perturbation state at row t0 for modes already started
+ *   (read when t0 > tsix_k), overwritten with the state at row t1 (for windowed runs).
+ *   yout_dev c128: row (t - t0)/out_every of the window for every t in [t0,t1) with
+ *   (t - t0) % out_every == 0, each row [nvar][nk]; out_every = 0 stores no trajectory.
+ *   flags_dev: int32, OR-ed with PF_FLAG_* (may be NULL). */
+int pf_fo_run(const pf_model *m, int64_t nk, const double *k_dev, const int64_t *tsix_dev,
+              const double *ystart_dev, const double *rec_dev, int64_t T, double h,
+              int64_t t0, int64_t t1, double *state_dev, double *yout_dev, int64_t out_every,
+              int32_t *flags_dev, void *stream);
+
+/* ---- K5: curvature power spectrum of trajectory rows (adiabatic.py:153-285) ----
+ * y_dev c128 [nrows][nvar][nk] -> Pr_dev [nrows][nk];  if k_dev != NULL the result is the
+ * scaled spectrum k^3/(2 pi^2) P_R (utilities.py:12-37). */
+int pf_pr_spectrum(int nfields, int64_t nrows, int64_t nk, const double *y_dev,
+                   const double *k_dev, double *Pr_dev, void *stream);
+
+/* ---- gather helper for the k-sharded multi-GPU layout ----
+ * Interleave a rank's slab [nrows][nvar][nk_r] into the global layout [nrows][nvar][nk] at
+ * column offset k0 (the on-GPU permute after an NCCL all-gather of slabs). */
+int pf_scatter_slab(int64_t nrows_times_nvar, int64_t nk_r, int64_t nk, int64_t k0,
+                    const double *slab_dev, double *full_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYFLATION_B200_H */

@@ -1,0 +1,73 @@
+"""analysis.adiabatic - curvature perturbation spectra (pyflation/analysis/adiabatic.py).
+
+``Pr`` / ``scaled_Pr`` accept a model whose ``yresult`` is a host NumPy array (reduced with
+NumPy, as post-processing) or a CUDA tensor (reduced on the device by ``pf_pr_spectrum``).
+"""
+import numpy as np
+
+from . import utilities
+
+
+def Pphi_matrix(modes, axis):
+    """P_IJ = sum_K chi_IK conj(chi_JK) for a mode matrix whose two nfields-long axes sit at
+    ``axis`` and ``axis+1``; result has the shape and dtype of ``modes``
+    (adiabatic.py:45-81)."""
+    modes = np.asarray(modes)
+    if axis < 0:
+        axis += modes.ndim - 1
+    m = np.moveaxis(modes, (axis, axis + 1), (0, 1))
+    P = np.einsum("ik...,jk...->ij...", m, m.conj())
+    return np.moveaxis(P, (0, 1), (axis, axis + 1)).astype(modes.dtype)
+
+
+def Pphi_modes(m):
+    """P_IJ flattened like ``m.yresult[:, m.dps_ix]`` (adiabatic.py:17-43)."""
+    mdp = utilities.getmodematrix(m.yresult, m.nfields, ix=1, ixslice=m.dps_ix)
+    return utilities.flattenmodematrix(Pphi_matrix(mdp, axis=1), m.nfields, 1, 2)
+
+
+def Pr_spectrum(phidot, modes, axis):
+    """P_R = sum_IJ phidot_I phidot_J P_IJ / (sum_K phidot_K^2)^2, real valued
+    (adiabatic.py:153-199)."""
+    phidot = np.atleast_1d(phidot)
+    modes = np.asarray(modes)
+    norm = (np.sum(phidot ** 2, axis=axis)) ** 2
+    weighted = (np.expand_dims(phidot, axis) * np.expand_dims(phidot, axis + 1)
+                * Pphi_matrix(modes, axis))
+    total = np.sum(weighted, axis=(axis, axis + 1))
+    return np.real(total / norm).astype(float)
+
+
+def _slices(m, tix, kix):
+    if tix is None:
+        tslice = slice(None)
+    else:
+        if tix < 0:
+            tix = len(m.tresult) + tix
+        tslice = slice(tix, tix + 1)
+    kslice = slice(None) if kix is None else slice(kix, kix + 1)
+    return tslice, kslice
+
+
+def Pr(m, tix=None, kix=None):
+    """Unscaled curvature power spectrum of model ``m`` for the requested rows and modes;
+    shape (rows, nk) (adiabatic.py:201-258)."""
+    tslice, kslice = _slices(m, tix, kix)
+    y = m.yresult[tslice, :, kslice]
+    if not isinstance(y, np.ndarray):                     # CUDA tensor -> K5
+        from .. import engine
+        return engine.pr_spectrum_device(m.nfields, y).cpu().numpy()
+    phidot = np.real(y[:, m.phidots_ix, :]).astype(np.float64)
+    modes = utilities.getmodematrix(y, m.nfields, ix=1, ixslice=m.dps_ix)
+    return Pr_spectrum(phidot, modes, 1)
+
+
+def scaled_Pr(m, tix=None, kix=None):
+    """k^3/(2 pi^2) P_R (adiabatic.py:261-285)."""
+    return utilities.kscaling(m.k, kix) * Pr(m, tix, kix)
+
+
+def findns(sPr, k, kix, running=False):
+    """Spectral index n_s (and running) of a scaled spectrum at ``k[kix]``
+    (adiabatic.py:84-131)."""
+    return utilities.spectral_index(sPr, k, kix, running)

@@ -1,0 +1,562 @@
+"""cosmomodels - drop-in model classes for the first-order path of ``pyflation.cosmomodels``.
+
+Class names, constructor signatures, ``.run()`` and the result attributes (``yresult``,
+``tresult``, ``k``, ``fotstart``, ``fotstartindex``, ``foystart``, ``ainit`` and the index
+slices ``H_ix, bg_ix, phis_ix, phidots_ix, pert_ix, dps_ix, dpdots_ix``) follow the reference
+(cosmomodels.py:53-206, 481-675, 973-1550, 2017-2197).  The integration itself is not done
+here: ``run()`` hands the model to :mod:`pyflation_b200.rk4`, which launches the CUDA kernels.
+
+Out of scope: second-order models, the HDF5 results files.
+"""
+import datetime
+import logging
+
+import numpy as np
+from scipy import interpolate
+
+from .configuration import _debug
+from . import cmpotentials
+from . import rk4
+from . import analysis
+
+module_logger = logging.getLogger(__name__)
+
+
+class ModelError(Exception):
+    """Generic error for model simulating. (cosmomodels.py:49)"""
+    pass
+
+
+class CosmologicalModel(object):
+    """Base class: argument checking, potential / solver lookup, ``run()``.
+    (cosmomodels.py:53-206)"""
+    solverlist = ["rkdriver_tsix"]
+
+    def __init__(self, ystart=None, simtstart=0.0, tstart=0.0, tstartindex=None,
+                 tend=83.0, tstep_wanted=0.01, solver="rkdriver_tsix",
+                 potential_func=None, pot_params=None, nfields=1, **kwargs):
+        self._log = logging.getLogger('%s.%s' % (__name__, self.__class__.__name__))
+        self.ystart = ystart
+        self.k = getattr(self, "k", None)
+
+        self.tstartindex = np.array([0]) if tstartindex is None else tstartindex
+
+        if np.all(tstart < tend):
+            self.tstart, self.tend = tstart, tend
+        elif np.all(tstart == tend):
+            raise ValueError("End time is the same as start time!")
+        else:
+            raise ValueError("Ending time is before starting time!")
+
+        if np.all(simtstart < tend):
+            self.simtstart = simtstart
+        elif simtstart == tend:
+            raise ValueError("End time is same a simulation start time!")
+        else:
+            raise ValueError("End time is before simulation start time!")
+
+        self.tstep_wanted = tstep_wanted
+
+        if solver not in self.solverlist:
+            raise ValueError("Solver not recognized!")
+        self.solver = solver
+
+        if potential_func is None:
+            potential_func = "msqphisq"
+        # AttributeError for an unknown name, like cmpotentials.__getattribute__ (:138)
+        self.potentials = getattr(cmpotentials, potential_func)
+        self.potential_func = potential_func
+
+        if pot_params is None:
+            pot_params = {}
+        if not isinstance(pot_params, dict):
+            raise ModelError("Need to provide pot_params as a dictionary of parameters.")
+        self.pot_params = pot_params
+
+        if nfields < 1:
+            raise ValueError("Cannot have zero or negative number of fields.")
+        self.nfields = nfields
+
+        self.tresult = None
+        self.yresult = None
+
+    def derivs(self, yarray, t):
+        """Right-hand side of the model's ODE system; subclasses name theirs."""
+        pass
+
+    def potentials(self, y, pot_params=None):
+        pass
+
+    def findH(self, potential, y):
+        pass
+
+    def run(self, saveresults=True):
+        """Execute a simulation run using the parameters already provided.
+        (cosmomodels.py:173-206)"""
+        if self.solver not in self.solverlist:
+            raise ModelError("Unknown solver!")
+        if not hasattr(self, "tstartindex"):
+            raise ModelError("Need to specify initial starting indices!")
+        if _debug:
+            self._log.debug("Starting simulation with %s.", self.solver)
+        solver = getattr(rk4, self.solver)
+        try:
+            self.tresult, self.yresult = solver(ystart=self.ystart,
+                                                simtstart=self.simtstart,
+                                                tsix=self.tstartindex,
+                                                tend=self.tend,
+                                                h=self.tstep_wanted,
+                                                derivs=self.derivs)
+        except Exception:
+            self._log.exception("Error running %s!", self.solver)
+            raise
+        self.lastparams = self.callingparams()
+        if saveresults:
+            try:
+                fname = self.saveallresults()
+                self._log.info("Results saved in " + fname)
+            except IOError as er:
+                self._log.error("Error trying to save results! Results NOT saved.\n" + str(er))
+        return
+
+    def callingparams(self):
+        """Dictionary of the parameters the run was called with."""
+        return {"tstart": self.tstart,
+                "tend": self.tend,
+                "tstep_wanted": self.tstep_wanted,
+                "solver": self.solver,
+                "classname": self.__class__.__name__,
+                "datetime": datetime.datetime.now().strftime("%Y%m%d%H%M%S"),
+                "nfields": self.nfields}
+
+    def saveallresults(self, filename=None, filetype="npz", **kwargs):
+        """Save results.  The reference writes a PyTables HDF5 file (cosmomodels.py:236-402);
+        that format is outside this package's scope, so the same dataset names are written to
+        a NumPy ``.npz`` archive instead."""
+        if self.yresult is None:
+            raise ModelError("No results to save yet.")
+        if filetype != "npz":
+            raise NotImplementedError("only filetype='npz' is available (HDF5 output is out of scope)")
+        if filename is None:
+            filename = "run" + datetime.datetime.now().strftime("%Y%m%d%H%M%S") + ".npz"
+        data = dict(yresult=self.yresult, tresult=self.tresult)
+        for name in ("k", "ystart", "bgystart", "foystart", "fotstart", "fotstartindex", "ainit"):
+            if getattr(self, name, None) is not None:
+                data[name] = np.asarray(getattr(self, name))
+        if getattr(self, "bgmodel", None) is not None:
+            data["bg_tresult"] = self.bgmodel.tresult
+            data["bg_yresult"] = self.bgmodel.yresult
+        np.savez(filename, **data)
+        return filename
+
+
+class PhiModels(CosmologicalModel):
+    """Models in the e-fold time scheme of Malik 06 (cosmomodels.py:474-522)."""
+
+    def findH(self, U, y):
+        """Hubble parameter from the Friedmann constraint, H^2 = U / (3 - phidot^2/2)."""
+        phidot = y[self.phidots_ix]
+        return np.sqrt(U / (3.0 - 0.5 * (np.sum(phidot ** 2))))
+
+    def getepsilon(self):
+        """epsilon = 1/2 sum_i phidot_i^2 for every stored row."""
+        if len(self.yresult.shape) == 3:
+            phidots = self.yresult[:, self.phidots_ix, 0]
+        else:
+            phidots = self.yresult[:, self.phidots_ix]
+        return 0.5 * np.sum(phidots ** 2, axis=1)
+
+    def findinflend(self):
+        """(efold, row index) of the end of inflation, epsilon >= 1; the efold is refined
+        with a cubic spline through the rows before it (cosmomodels.py:493-511)."""
+        self.epsilon = self.getepsilon()
+        if not any(self.epsilon > 1):
+            raise ModelError("Inflation did not end during specified number of efoldings. "
+                             "Increase tend and try again!")
+        endindex = np.where(self.epsilon >= 1)[0][0]
+        tck = interpolate.splrep(self.tresult[:endindex], self.epsilon[:endindex])
+        t2 = np.linspace(self.tresult[endindex - 1], self.tresult[endindex], 100)
+        y2 = interpolate.splev(t2, tck)
+        endefold = t2[np.where(y2 > 1)[0][0]]
+        return endefold, endindex
+
+
+def _device_only(name):
+    raise NotImplementedError(
+        "%s is evaluated inside the CUDA kernels (csrc/pf_bg.cu, csrc/pf_fo.cu); it is not "
+        "callable from Python and there is no CPU implementation in this package" % name)
+
+
+class CanonicalBackground(PhiModels):
+    """Background model in e-fold time: y = (phi_i, dphi_i/dn, ..., H).
+    (cosmomodels.py:525-571)"""
+
+    def __init__(self, *args, **kwargs):
+        super(CanonicalBackground, self).__init__(*args, **kwargs)
+        self.H_ix = self.nfields * 2
+        self.bg_ix = slice(0, self.nfields * 2 + 1)
+        self.phis_ix = slice(0, self.nfields * 2, 2)
+        self.phidots_ix = slice(1, self.nfields * 2, 2)
+        if np.all(self.ystart[self.H_ix] == 0.0):
+            U = self.potentials(self.ystart, self.pot_params)[0]
+            self.ystart[self.H_ix] = self.findH(U, self.ystart)
+
+    def derivs(self, y, t, **kwargs):
+        """Background equations of motion -- device code (pf_bg.cu: bg_rhs)."""
+        _device_only("CanonicalBackground.derivs")
+
+
+class CanonicalFirstOrder(PhiModels):
+    """First order model: background rows, H, then the nfields x nfields complex mode matrix
+    and its e-fold derivative, interleaved (cosmomodels.py:573-675)."""
+
+    def __init__(self, k=None, ainit=None, *args, **kwargs):
+        super(CanonicalFirstOrder, self).__init__(*args, **kwargs)
+        self.ainit = 1 if ainit is None else ainit
+        self.k = 10 ** (np.arange(10.0) - 8) if k is None else k
+        self.setfieldindices()
+        if self.ystart is None:
+            self.ystart = np.array([18.0, -0.1] * self.nfields + [0.0] + [1.0, 0.0] * self.nfields)
+        if np.all(self.ystart[self.H_ix] == 0.0):
+            U = self.potentials(self.ystart, self.pot_params)[0]
+            self.ystart[self.H_ix] = self.findH(U, self.ystart)
+
+    def setfieldindices(self):
+        nf = self.nfields
+        self.H_ix = nf * 2
+        self.bg_ix = slice(0, nf * 2 + 1)
+        self.phis_ix = slice(0, nf * 2, 2)
+        self.phidots_ix = slice(1, nf * 2, 2)
+        self.pert_ix = slice(nf * 2 + 1, None)
+        self.dps_ix = slice(nf * 2 + 1, None, 2)
+        self.dpdots_ix = slice(nf * 2 + 2, None, 2)
+
+    def derivs(self, y, t, **kwargs):
+        """First order equations of motion -- device code (pf_fo.cu: mode_rhs)."""
+        _device_only("CanonicalFirstOrder.derivs")
+
+
+class MultiStageDriver(CosmologicalModel):
+    """Parent of the multi-stage drivers: horizon crossing and post-inflation bookkeeping.
+    (cosmomodels.py:973-1227)"""
+
+    def __init__(self, *args, **kwargs):
+        super(MultiStageDriver, self).__init__(*args, **kwargs)
+        self.cq = kwargs["cq"] if "cq" in kwargs else 50
+
+    def find_efolds_after_inflation(self, Hend, Hreh=None):
+        """Efolds from the end of inflation until today (instant reheating by default)."""
+        if Hreh is None:
+            Hreh = Hend
+        return 72.3 + 2.0 / 3.0 * np.log(Hend) - 1.0 / 6.0 * np.log(Hreh)
+
+    def finda_end(self, Hend, Hreh=None, a_0=1):
+        return a_0 * np.exp(-self.find_efolds_after_inflation(Hend, Hreh))
+
+    def finda_0(self, Hend, Hreh=None, a_end=None):
+        if a_end is None:
+            try:
+                a_end = self.ainit * np.exp(self.tresult[-1])
+            except TypeError:
+                raise ModelError("Simulation has not been run yet.")
+        return a_end * np.exp(self.find_efolds_after_inflation(Hend, Hreh))
+
+    def _crossing_rows(self, k, t, H, factor=None):
+        """First row of ``t`` with ``k < factor*a*H`` for every k at once.
+
+        The reference scans ``np.where(np.sign(k - factor*aH) < 0)[0][0]`` per mode in a
+        Python loop (cosmomodels.py:1108, 1131).  The first index at which a sequence exceeds k
+        is also the first index at which its running maximum does, and the running maximum is
+        sorted, so one ``searchsorted`` gives the same rows in O(nk log T)."""
+        if factor is None:
+            factor = self.cq
+        H = np.asarray(H)
+        if len(H.shape) > 1:
+            H = H[:, 0]
+        aH = factor * (self.ainit * np.exp(t) * H)
+        rows = np.searchsorted(np.maximum.accumulate(aH), np.atleast_1d(k), side="right")
+        late = rows >= len(aH)
+        if np.any(late):
+            raise ModelError("k mode " + str(np.atleast_1d(k)[late][0])
+                             + " crosses horizon after end of inflation!")
+        return rows
+
+    def findkcrossing(self, k, t, H, factor=None):
+        """(row index, efold) at which one mode satisfies k = factor*a*H."""
+        row = int(self._crossing_rows(k, t, H, factor)[0])
+        return row, t[row]
+
+    def findallkcrossings(self, t, H):
+        """Array of (row index, efold) pairs for every k in ``self.k``."""
+        rows = self._crossing_rows(self.k, t, H)
+        return np.column_stack((rows.astype(float), t[rows]))
+
+    def findHorizoncrossings(self, factor=1):
+        """(row, efold) of k = factor*a*H for every mode, from the first-order results."""
+        H = np.real(self.yresult[:, self.H_ix, :])
+        out = []
+        for onek, oneH in zip(self.k, np.rollaxis(H, -1, 0)):
+            aH = self.ainit * np.exp(self.tresult) * oneH
+            hit = np.where(np.sign(onek - factor * aH) < 0)[0]
+            if hit.size == 0:
+                raise ModelError("k mode " + str(onek) + " crosses horizon after end of inflation!")
+            out.append((hit[0], self.tresult[hit[0]]))
+        return np.array(out)
+
+    @property
+    def Pr(self):
+        """Unscaled power spectrum of the comoving curvature perturbation, all rows and k."""
+        return analysis.Pr(self)
+
+    @property
+    def scaled_Pr(self):
+        """k^3/(2 pi^2) P_R for all rows and k."""
+        return analysis.scaled_Pr(self)
+
+    @property
+    def Pzeta(self):
+        raise NotImplementedError("Pzeta belongs to the non-adiabatic analysis (out of scope)")
+
+    @property
+    def scaled_Pzeta(self):
+        raise NotImplementedError("scaled_Pzeta belongs to the non-adiabatic analysis (out of scope)")
+
+    def getfoystart(self):
+        pass
+
+    def callingparams(self):
+        try:
+            self.k
+        except (NameError, AttributeError):
+            self.k = None
+        return {"tstart": self.tstart,
+                "ainit": self.ainit,
+                "potential_func": self.potentials.__name__,
+                "tend": self.tend,
+                "tstep_wanted": self.tstep_wanted,
+                "solver": self.solver,
+                "classname": self.__class__.__name__,
+                "datetime": datetime.datetime.now().strftime("%Y%m%d%H%M%S"),
+                "nfields": self.nfields}
+
+
+class FOCanonicalTwoStage(MultiStageDriver):
+    """Background run -> initial conditions -> first-order run (cosmomodels.py:1229-1550)."""
+
+    def __init__(self, bgystart=None, tstart=0.0, tstartindex=None, tend=83.0, tstep_wanted=0.01,
+                 k=None, ainit=None, solver="rkdriver_tsix", bgclass=None, foclass=None,
+                 potential_func=None, pot_params=None, simtstart=0, nfields=1, **kwargs):
+        if bgystart is None:
+            self.bgystart = np.array([18.0 / np.sqrt(nfields), -0.1 / np.sqrt(nfields)] * nfields
+                                     + [0.0])
+        else:
+            self.bgystart = bgystart
+        self.ystart = np.append(self.bgystart, [0.0, 0.0] * nfields ** 2)
+        self.tstartindex = tstartindex if tstartindex else np.array([0])
+        super(FOCanonicalTwoStage, self).__init__(
+            ystart=self.ystart, tstart=tstart, tstartindex=self.tstartindex, tend=tend,
+            tstep_wanted=tstep_wanted, solver=solver, potential_func=potential_func,
+            pot_params=pot_params, nfields=nfields, **kwargs)
+        self.setfieldindices()
+        self.ainit = 1 if ainit is None else ainit
+        self.k = 10 ** (np.arange(7.0) - 62) if k is None else k
+        self.simtstart = simtstart
+        self.bgclass = CanonicalBackground if bgclass is None else bgclass
+        self.foclass = CanonicalFirstOrder if foclass is None else foclass
+        self.bgmodel = self.firstordermodel = None
+
+    def setfieldindices(self):
+        nf = self.nfields
+        self.H_ix = nf * 2
+        self.bg_ix = slice(0, nf * 2 + 1)
+        self.phis_ix = slice(0, nf * 2, 2)
+        self.phidots_ix = slice(1, nf * 2, 2)
+        self.pert_ix = slice(nf * 2 + 1, None)
+        self.dps_ix = slice(nf * 2 + 1, None, 2)
+        self.dpdots_ix = slice(nf * 2 + 2, None, 2)
+
+    def _choose_ainit(self):
+        Hend = self.bgmodel.yresult[self.fotendindex, self.H_ix]
+        self.a_end = self.finda_end(Hend)
+        return self.a_end * np.exp(-self.bgmodel.tresult[self.fotendindex])
+
+    def setfoics(self):
+        """Initial conditions of the first-order run from the finished background run.
+        (cosmomodels.py:1307-1341)"""
+        self.ainit = self._choose_ainit()
+        if not hasattr(self, "bgepsilon"):
+            self.bgepsilon = self.bgmodel.getepsilon()
+        self.etainit = -1 / (self.ainit * self.bgmodel.yresult[0, self.H_ix] * (1 - self.bgepsilon[0]))
+        kcrossings = self.findallkcrossings(self.bgmodel.tresult[:self.fotendindex],
+                                            self.bgmodel.yresult[:self.fotendindex, self.H_ix])
+        kcrossefolds = kcrossings[:, 1]
+        if np.any(kcrossefolds == 0):
+            raise ModelError("Some k modes crossed horizon before simulation began and cannot "
+                             "be initialized!")
+        self.fotstart, self.fotstartindex = kcrossefolds, kcrossings[:, 0].astype(int)
+        self.foystart = self.getfoystart()
+        return
+
+    def runbg(self):
+        """Run the background model and find the end of inflation (cosmomodels.py:1343-1374)."""
+        if len(self.ystart.shape) == 1:
+            ys = self.ystart[self.bg_ix]
+        elif len(self.ystart.shape) == 2:
+            ys = self.ystart[self.bg_ix, 0]
+        self.bgmodel = self.bgclass(ystart=ys, tstart=self.tstart, tstartindex=np.array([0]),
+                                    tend=self.tend, tstep_wanted=self.tstep_wanted,
+                                    solver=self.solver, potential_func=self.potential_func,
+                                    pot_params=self.pot_params, nfields=self.nfields)
+        self._log.info("Running background model...")
+        try:
+            self.bgmodel.run(saveresults=False)
+        except ModelError:
+            self._log.exception("Error in background run, aborting!")
+        self.fotend, self.fotendindex = self.bgmodel.findinflend()
+        self._log.info("Background run complete, inflation ended " + str(self.fotend)
+                       + " efoldings after start.")
+        return
+
+    def runfo(self):
+        """Run the first order model (cosmomodels.py:1376-1404)."""
+        self.firstordermodel = self.foclass(ystart=self.foystart, tstart=self.fotstart,
+                                            simtstart=self.simtstart,
+                                            tstartindex=self.fotstartindex, tend=self.fotend,
+                                            tstep_wanted=self.tstep_wanted, solver=self.solver,
+                                            k=self.k, ainit=self.ainit,
+                                            potential_func=self.potential_func,
+                                            pot_params=self.pot_params, nfields=self.nfields)
+        self._log.info("Beginning first order run...")
+        try:
+            self.firstordermodel.run(saveresults=False)
+        except ModelError as er:
+            raise ModelError("Error in first order run, aborting! Message: " + str(er))
+        self.tresult, self.yresult = self.firstordermodel.tresult, self.firstordermodel.yresult
+        return
+
+    def run(self, saveresults=True):
+        """Background run, initial conditions, first-order run (cosmomodels.py:1406-1441)."""
+        self.runbg()
+        self.setfoics()
+        self.runfo()
+        self.lastparams = self.callingparams()
+        if saveresults:
+            try:
+                self._log.info("Results saved in " + self.saveallresults())
+            except IOError:
+                self._log.exception("Error trying to save results! Results NOT saved.")
+        return
+
+    # ---- Bunch-Davies initial conditions --------------------------------------------------
+    def _ic_inputs(self, ts, tsix):
+        if ts is None or tsix is None:
+            ts, tsix = self.fotstart, self.fotstartindex
+        bgy = self.bgmodel.yresult
+        if len(bgy.shape) > 2:
+            bgy = bgy[..., 0]
+        nvar = 2 * self.nfields ** 2 + self.nfields * 2 + 1
+        foystart = np.zeros((nvar, len(self.k)), dtype=np.complex128)
+        foystart[self.bg_ix] = bgy[tsix, :].transpose()
+        astar = self.ainit * np.exp(ts)
+        Hstar = bgy[tsix, self.H_ix]
+        return ts, tsix, bgy, foystart, astar, Hstar
+
+    def _phase(self, tsix, bgy, astar, Hstar):
+        """exp(-i k (eta_* - eta_init)) with eta = -1/(a H (1 - epsilon))."""
+        etastar = -1 / (astar * Hstar * (1 - self.bgepsilon[tsix]))
+        try:
+            etadiff = etastar - self.etainit
+        except AttributeError:
+            etadiff = etastar + 1 / (self.ainit * bgy[0, self.H_ix] * (1 - self.bgepsilon[0]))
+        return np.exp(-(self.k * etadiff) * 1j)
+
+    def _fill_diagonal(self, foystart, dp, dpdot, skip=None):
+        nf = self.nfields
+        nb = 2 * nf + 1
+        for i in range(nf):
+            if skip is not None and i == skip:
+                continue
+            foystart[nb + 2 * (i * nf + i)] = dp
+            foystart[nb + 2 * (i * nf + i) + 1] = dpdot
+
+    def getfoystart(self, ts=None, tsix=None):
+        """Start vector of every mode: background rows at its start row, diagonal mode-matrix
+        entries in the Bunch-Davies state, off-diagonals zero (cosmomodels.py:1443-1492)."""
+        ts, tsix, bgy, foystart, astar, Hstar = self._ic_inputs(ts, tsix)
+        arootk = 1 / (astar * (np.sqrt(2 * self.k)))
+        osc = self._phase(tsix, bgy, astar, Hstar)
+        self._fill_diagonal(foystart, arootk * osc,
+                            -arootk * osc * (1 + (self.k / (astar * Hstar)) * 1j))
+        return foystart
+
+    def getdeltaphi(self):
+        return self.deltaphi
+
+    def deltaphi(self, recompute=False):
+        """delta phi mode matrix rows for all rows and k (cosmomodels.py:1497-1520)."""
+        if not hasattr(self, "_deltaphi") or recompute:
+            self._deltaphi = self.yresult[:, self.dps_ix, :]
+        return self._deltaphi
+
+    @property
+    def phis(self):
+        return self.yresult[:, self.phis_ix]
+
+    @property
+    def phidots(self):
+        return self.yresult[:, self.phidots_ix]
+
+    @property
+    def H(self):
+        return self.yresult[:, self.H_ix]
+
+    @property
+    def dpmodes(self):
+        return self.yresult[:, self.dps_ix]
+
+    @property
+    def dpdotmodes(self):
+        return self.yresult[:, self.dpdots_ix]
+
+    @property
+    def a(self):
+        return self.ainit * np.exp(self.tresult)
+
+
+class FixedainitTwoStage(FOCanonicalTwoStage):
+    """First order driver with ainit fixed by the caller (cosmomodels.py:2017-2073)."""
+
+    def __init__(self, *args, **kwargs):
+        super(FixedainitTwoStage, self).__init__(*args, **kwargs)
+        # default: ainit of the standard msqphisq run (cosmomodels.py:2043)
+        self.fixedainit = kwargs["ainit"] if "ainit" in kwargs else 7.837219134630212e-65
+
+    def _choose_ainit(self):
+        return self.fixedainit
+
+
+class FONoPhase(FOCanonicalTwoStage):
+    """Initial conditions without the exp(-i k eta) phase (cosmomodels.py:2076-2132)."""
+
+    def getfoystart(self, ts=None, tsix=None):
+        ts, tsix, bgy, foystart, astar, Hstar = self._ic_inputs(ts, tsix)
+        arootk = 1 / (astar * (np.sqrt(2 * self.k)))
+        self._fill_diagonal(foystart, arootk, -arootk * (1 + (self.k / (astar * Hstar)) * 1j))
+        return foystart
+
+
+class FOSuppressOneField(FOCanonicalTwoStage):
+    """Standard initial conditions with one field's mode switched off (cosmomodels.py:2135-2197)."""
+
+    def __init__(self, suppress_ix=0, *args, **kwargs):
+        self.suppress_ix = suppress_ix
+        super(FOSuppressOneField, self).__init__(*args, **kwargs)
+
+    def getfoystart(self, ts=None, tsix=None):
+        ts, tsix, bgy, foystart, astar, Hstar = self._ic_inputs(ts, tsix)
+        arootk = 1 / (astar * (np.sqrt(2 * self.k)))
+        osc = self._phase(tsix, bgy, astar, Hstar)
+        self._fill_diagonal(foystart, arootk * osc,
+                            -arootk * osc * (1 + (self.k / (astar * Hstar)) * 1j),
+                            skip=self.suppress_ix)
+        return foystart

@@ -1,0 +1,172 @@
+// C-ABI glue: error text, potential table, size helpers, P_R reduction (K5) and the slab
+// interleave used after a multi-GPU gather.  See include/pyflation_b200.h.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "pf_common.cuh"
+
+namespace pf {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* where) {
+    set_error("%s: CUDA error %d (%s)", where, (int)e, cudaGetErrorString(e));
+    return (int)e;
+}
+
+struct PotInfo {
+    const char* name;
+    int nfields;  // 0 = any
+    int nparams;
+    const char* pname[PF_MAX_PARAMS];
+    double pdefault[PF_MAX_PARAMS];
+};
+
+// names and defaults: pyflation/cmpotentials.py (lines in include/pyflation_b200.h)
+static const PotInfo kPot[PF_NUM_POTENTIALS] = {
+    {"msqphisq", 1, 1, {"mass"}, {6.3267e-6}},
+    {"lambdaphi4", 1, 1, {"lambda"}, {1.5506e-13}},
+    {"linde", 1, 2, {"mass", "lambda"}, {5e-8, 1.55009e-13}},
+    {"hybrid2and4", 1, 2, {"mass", "lambda"}, {5e-8, 1.55123e-13}},
+    {"phi2over3", 1, 1, {"sigma"}, {3.81686e-10}},
+    {"msqphisq_withV0", 1, 2, {"mass", "V0"}, {1.7403553e-06, 5e-10}},
+    {"step_potential", 1, 4, {"mass", "c", "d", "phi_s"}, {6.3267e-6, 0.0018, 0.022, 14.84}},
+    {"bump_potential", 1, 4, {"mass", "c", "d", "phi_b"}, {6.3267e-6, 0.0005, 0.01, 14.84}},
+    {"resonance", 1, 3, {"mass", "c", "d"}, {6.3267e-6, 5e-7, 0.0007}},
+    {"bump_nothirdderiv", 1, 4, {"mass", "c", "d", "phi_b"}, {6.3267e-6, 0.0005, 0.01, 14.84}},
+    {"hybridquadratic", 2, 2, {"m1", "m2"}, {1.395464769e-6, 9.768253382e-6}},
+    {"ridge_twofield", 2, 3, {"g", "m", "V0"}, {1e-5, 12e-5, 1.0}},
+    {"nflation", 0, 1, {"mass"}, {6.3267e-6}},
+    {"quartictwofield", 2, 4, {"m1", "m2", "l1", "l2"}, {5e-6, 5e-8, 5e-10, 5e-14}},
+    {"hybridquartic", 2, 4, {"lambda", "v", "mu", "phi_c"}, {2.3644e-6, 0.1, 1e3, 0.01}},
+    {"inflection", 2, 4, {"lambda", "g", "r", "m"}, {3e3, 3e-2, 0.14, 1.0}},
+    {"hilltopaxion", 2, 3, {"Lambda", "f", "m"}, {6.90988298942670958e-4, 1.0, 6e-6}},
+    {"productexponential", 2, 2, {"lambda", "V_0"}, {0.05, 5.3705e-13}},
+};
+
+int check_model(const pf_model* m) {
+    if (!m) { set_error("null pf_model"); return PF_E_ARG; }
+    if (m->potential_id < 0 || m->potential_id >= PF_NUM_POTENTIALS) {
+        set_error("unknown potential id %d", m->potential_id);
+        return PF_E_POTENTIAL;
+    }
+    if (m->nfields < 1 || m->nfields > PF_MAX_NFIELDS) {
+        set_error("nfields=%d outside 1..%d", m->nfields, PF_MAX_NFIELDS);
+        return PF_E_NFIELDS;
+    }
+    const int want = kPot[m->potential_id].nfields;
+    if (want != 0 && want != m->nfields) {
+        set_error("potential %s is defined for nfields=%d, not %d", kPot[m->potential_id].name, want,
+                  m->nfields);
+        return PF_E_POTENTIAL;
+    }
+    return PF_OK;
+}
+
+// P_R = sum_K |sum_I phi'_I chi_IK|^2 / (sum_K phi'_K^2)^2     adiabatic.py:153-199
+// thread <-> (row, k); reads are coalesced along k.
+__global__ void pr_kernel(int nf, int64_t nrows, int64_t nk, const double2* __restrict__ y,
+                          const double* __restrict__ kgrid, double* __restrict__ Pr) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t row = blockIdx.y;
+    if (k >= nk || row >= nrows) return;
+    const int nvar = nvar_of(nf), nb = nbg_of(nf);
+    const double2* yr = y + row * (int64_t)nvar * nk + k;
+    double pd[PF_MAX_NFIELDS];
+    double norm = 0.0;
+    for (int i = 0; i < nf; ++i) {
+        pd[i] = yr[(int64_t)(2 * i + 1) * nk].x;          // adiabatic.py:253 keeps the real part
+        norm += pd[i] * pd[i];
+    }
+    double total = 0.0;
+    for (int K = 0; K < nf; ++K) {
+        double re = 0.0, im = 0.0;
+        for (int I = 0; I < nf; ++I) {
+            const double2 chi = yr[(int64_t)(nb + 2 * (I * nf + K)) * nk];
+            re += pd[I] * chi.x;
+            im += pd[I] * chi.y;
+        }
+        total += re * re + im * im;
+    }
+    double out = total / (norm * norm);
+    if (kgrid) {
+        const double kk = kgrid[k];
+        out *= kk * kk * kk / (2.0 * 3.141592653589793 * 3.141592653589793);   // utilities.py:37
+    }
+    Pr[row * nk + k] = out;
+}
+
+}  // namespace pf
+
+using namespace pf;
+
+extern "C" int pf_version(void) { return PF_ABI_VERSION; }
+extern "C" const char* pf_last_error(void) { return g_err; }
+
+extern "C" int pf_potential_id(const char* name) {
+    if (!name) return -1;
+    for (int i = 0; i < PF_NUM_POTENTIALS; ++i)
+        if (strcmp(kPot[i].name, name) == 0) return i;
+    return -1;
+}
+extern "C" const char* pf_potential_name(int id) {
+    return (id >= 0 && id < PF_NUM_POTENTIALS) ? kPot[id].name : nullptr;
+}
+extern "C" int pf_potential_nfields(int id) {
+    return (id >= 0 && id < PF_NUM_POTENTIALS) ? kPot[id].nfields : -1;
+}
+extern "C" int pf_potential_nparams(int id) {
+    return (id >= 0 && id < PF_NUM_POTENTIALS) ? kPot[id].nparams : -1;
+}
+extern "C" const char* pf_potential_param_name(int id, int i) {
+    if (id < 0 || id >= PF_NUM_POTENTIALS || i < 0 || i >= kPot[id].nparams) return nullptr;
+    return kPot[id].pname[i];
+}
+extern "C" double pf_potential_param_default(int id, int i) {
+    if (id < 0 || id >= PF_NUM_POTENTIALS || i < 0 || i >= kPot[id].nparams) return NAN;
+    return kPot[id].pdefault[i];
+}
+
+extern "C" int64_t pf_number_of_steps(double simtstart, double tend, double h) {
+    // int(np.around((tend - simtstart)/h) + 1): around = round-half-to-even = nearbyint
+    return (int64_t)(nearbyint((tend - simtstart) / h) + 1.0);
+}
+extern "C" int64_t pf_nvar(int nfields) { return nvar_of(nfields); }
+extern "C" int64_t pf_rec_doubles(int nfields) { return rec_of(nfields); }
+
+extern "C" int pf_pr_spectrum(int nfields, int64_t nrows, int64_t nk, const double* y_dev,
+                              const double* k_dev, double* Pr_dev, void* stream) {
+    if (nfields < 1 || nfields > PF_MAX_NFIELDS) { set_error("pf_pr_spectrum: nfields=%d", nfields); return PF_E_NFIELDS; }
+    if (nrows < 0 || nk < 0) { set_error("pf_pr_spectrum: negative size"); return PF_E_ARG; }
+    if (nrows == 0 || nk == 0) return PF_OK;
+    if (!y_dev || !Pr_dev) { set_error("pf_pr_spectrum: null buffer"); return PF_E_ARG; }
+    if (nrows > 65535) { set_error("pf_pr_spectrum: at most 65535 rows per call"); return PF_E_ARG; }
+    const int block = 128;
+    dim3 grid((unsigned)((nk + block - 1) / block), (unsigned)nrows, 1);
+    pr_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(nfields, nrows, nk, (const double2*)y_dev, k_dev, Pr_dev);
+    PF_CUDA_CHECK(cudaGetLastError(), "pf_pr_spectrum launch");
+    return PF_OK;
+}
+
+extern "C" int pf_scatter_slab(int64_t nrows_times_nvar, int64_t nk_r, int64_t nk, int64_t k0,
+                               const double* slab_dev, double* full_dev, void* stream) {
+    if (nrows_times_nvar < 0 || nk_r < 0 || nk < nk_r || k0 < 0 || k0 + nk_r > nk) {
+        set_error("pf_scatter_slab: bad sizes");
+        return PF_E_ARG;
+    }
+    if (nrows_times_nvar == 0 || nk_r == 0) return PF_OK;
+    if (!slab_dev || !full_dev) { set_error("pf_scatter_slab: null buffer"); return PF_E_ARG; }
+    PF_CUDA_CHECK(cudaMemcpy2DAsync(full_dev + 2 * k0, (size_t)nk * 16, slab_dev, (size_t)nk_r * 16,
+                                    (size_t)nk_r * 16, (size_t)nrows_times_nvar,
+                                    cudaMemcpyDeviceToDevice, (cudaStream_t)stream),
+                  "pf_scatter_slab");
+    return PF_OK;
+}

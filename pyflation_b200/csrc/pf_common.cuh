@@ -1,0 +1,31 @@
+// Shared host/device helpers for the pyflation_b200 C-ABI library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/pyflation_b200.h"
+
+namespace pf {
+
+// thread-local error text behind pf_last_error()
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* where);
+
+#define PF_CUDA_CHECK(expr, where)                         \
+    do {                                                   \
+        cudaError_t _e = (expr);                           \
+        if (_e != cudaSuccess) return pf::cuda_fail(_e, where); \
+    } while (0)
+
+__host__ __device__ constexpr int nvar_of(int nf) { return 2 * nf * nf + 2 * nf + 1; }
+__host__ __device__ constexpr int nbg_of(int nf) { return 2 * nf + 1; }
+// record = bg row (2nf+1) + 4 stages x (A, R, C[nf][nf]), padded to an even number of doubles
+__host__ __device__ constexpr int rec_of(int nf) {
+    return ((2 * nf + 1 + 4 * (2 + nf * nf)) + 1) & ~1;
+}
+
+__device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+int check_model(const pf_model* m);
+
+}  // namespace pf

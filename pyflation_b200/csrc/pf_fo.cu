@@ -1,0 +1,360 @@
+// K2/K3 : fixed-step RK4 of the complex first-order mode matrix over a batch of k modes,
+//         each mode starting at its own row, writing the reference's trajectory layout.
+//
+// Replaces rk4.rkdriver_tsix (rk4.py:58-138) + rk4stepks (:27-55) driving
+// CanonicalFirstOrder.derivs (cosmomodels.py:625-675).
+//
+// Formulation (DESIGN.md "K2/K3"): the background is shared by every mode, so its rows and the
+// k-independent factors of the right-hand side come from the per-step records built by
+// pf_stage_table (A = U/H^2, R = 1/(aH), C = M/H^2 at each RK4 stage).  What is left per mode
+// and per column j of the mode matrix is the real-coefficient linear system
+//     x' = v,   v' = -(A v + (k R)^2 x + C x),      x = dphi_{.j},  v = dphi'_{.j}
+// whose real and imaginary parts never mix.  One thread owns one (k, j) pair (NC = 2, complex
+// in registers) or one (k, j, re|im) triple (NC = 1, used for nf >= 3 to fit the register
+// file); all RK4 stage vectors stay in registers.  Consecutive lanes hold consecutive k, so
+// every row store of a warp is one contiguous 512-byte (NC = 2: 128-bit per lane) or
+// 256-byte (NC = 1: 64-bit per lane) segment of yresult[t][var][:].
+//
+// The records are streamed through shared memory in double-buffered chunks with 1-D TMA bulk
+// copies (cp.async.bulk + mbarrier complete_tx); every thread of the CTA reads the same record,
+// i.e. conflict-free broadcast loads.
+#include "pf_common.cuh"
+
+namespace pf {
+
+struct FoArgs {
+    int64_t nk;
+    const double* __restrict__ k;
+    const int64_t* __restrict__ tsix;
+    const double* __restrict__ ystart;   // c128 [nvar][nk]
+    const double* __restrict__ rec;      // [T][REC]
+    int64_t T, t0, t1;
+    double* __restrict__ state;          // c128 [2 nf^2][nk]
+    double* __restrict__ yout;           // c128 [rows][nvar][nk]
+    int64_t out_every;
+    int32_t* flags;
+    double h;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <int NF>
+struct FoShape {
+    static constexpr int NB = 2 * NF + 1;
+    static constexpr int SW = 2 + NF * NF;          // doubles per stage: A, R, C[NF][NF]
+    static constexpr int REC = rec_of(NF);
+    static constexpr int BG_OFF = 4 * SW;           // background row sits after the 4 stages
+    static constexpr int CH_RAW = 16384 / (REC * 8);
+    static constexpr int CH = CH_RAW > 64 ? 64 : (CH_RAW < 8 ? 8 : CH_RAW);  // steps per chunk
+    static constexpr int BLOCK = 128;
+};
+
+// one complex (NC = 2) or one real component (NC = 1) per row, per thread
+template <int NC>
+__device__ __forceinline__ void store_row(double* rowbase, int64_t kk, int part, const double (&c)[NC]) {
+    if constexpr (NC == 2) {
+        __stcs(reinterpret_cast<double2*>(rowbase) + kk, make_double2(c[0], c[1]));
+    } else {
+        __stcs(rowbase + 2 * kk + part, c[0]);
+    }
+}
+
+// kv = -(A v + (kR)^2 x + C x)        cosmomodels.py:663-674
+template <int NF, int NC>
+__device__ __forceinline__ void mode_rhs(const double* __restrict__ cs, double kval,
+                                         const double (&x)[NF][NC], const double (&v)[NF][NC],
+                                         double (&kv)[NF][NC]) {
+    const double A = cs[0];
+    const double kr = kval * cs[1];
+    const double B = kr * kr;
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            double acc = A * v[i][c];
+            acc = fma(B, x[i][c], acc);
+#pragma unroll
+            for (int l = 0; l < NF; ++l) acc = fma(cs[2 + i * NF + l], x[l][c], acc);
+            kv[i][c] = -acc;
+        }
+    }
+}
+
+template <int NF, int NC>
+__global__ void __launch_bounds__(FoShape<NF>::BLOCK) fo_rk4_kernel(FoArgs a) {
+    using S = FoShape<NF>;
+    constexpr int NB = S::NB, SW = S::SW, REC = S::REC, CH = S::CH, NV = nvar_of(NF);
+    constexpr int KPB = S::BLOCK / (3 - NC);        // k modes per CTA
+
+    __shared__ __align__(128) double srec[2][CH * REC];
+    __shared__ __align__(8) uint64_t bars[2];
+
+    const int tid = threadIdx.x;
+    const int part = (NC == 2) ? 0 : (tid & 1);
+    const int kl = (NC == 2) ? tid : (tid >> 1);
+    const int64_t kk = (int64_t)blockIdx.x * KPB + kl;
+    const int j = blockIdx.y;
+    const bool live = kk < a.nk;
+    const int64_t nk = a.nk;
+
+    const int64_t nsteps = a.t1 - a.t0;
+    const int64_t nchunks = (nsteps + CH - 1) / CH;
+
+    auto issue = [&](int64_t c) {
+        const int buf = (int)(c & 1);
+        const int64_t base = a.t0 + c * CH;
+        const int64_t cnt = (a.t1 - base) < CH ? (a.t1 - base) : CH;
+        const uint32_t bytes = (uint32_t)(cnt * REC * sizeof(double));
+        mbar_expect_tx(&bars[buf], bytes);
+        bulk_g2s(&srec[buf][0], a.rec + base * REC, bytes, &bars[buf]);
+    };
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (nchunks > 0) issue(0);
+        if (nchunks > 1) issue(1);
+    }
+
+    const double kval = live ? a.k[kk] : 0.0;
+    const int64_t ts = live ? a.tsix[kk] : INT64_MAX;
+    const double h = a.h, hh = h * 0.5, h6 = h / 6.0;   // rk4.py:31-32
+    const double nan = qnan();
+
+    double x[NF][NC], v[NF][NC];
+#pragma unroll
+    for (int i = 0; i < NF; ++i)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { x[i][c] = 0.0; v[i][c] = 0.0; }
+
+    if (live && a.t0 > ts) {                          // resume a windowed run
+#pragma unroll
+        for (int i = 0; i < NF; ++i) {
+            const double* sx = a.state + 2 * ((int64_t)(2 * (i * NF + j)) * nk + kk);
+            const double* sv = a.state + 2 * ((int64_t)(2 * (i * NF + j) + 1) * nk + kk);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) { x[i][c] = sx[part + c]; v[i][c] = sv[part + c]; }
+        }
+    }
+
+    int64_t next_out = (a.yout != nullptr && a.out_every > 0) ? a.t0 : INT64_MAX;
+    double* orow = a.yout;                            // start of the current output row block
+
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int buf = (int)(c & 1);
+        mbar_wait(&bars[buf], (uint32_t)((c >> 1) & 1));
+        const int64_t base = a.t0 + c * CH;
+        const int cnt = (int)((a.t1 - base) < CH ? (a.t1 - base) : CH);
+        for (int q = 0; q < cnt; ++q) {
+            const int64_t n = base + q;
+            const double* __restrict__ r = &srec[buf][q * REC];
+            const bool out = (n == next_out);
+            if (n < ts) {
+                // rows before this mode's start stay NaN+NaNj        rk4.py:100
+                if (out && live) {
+                    double nn[NC];
+#pragma unroll
+                    for (int cc = 0; cc < NC; ++cc) nn[cc] = nan;
+                    store_row<NC>(orow + 2 * (int64_t)(2 * j) * nk, kk, part, nn);
+                    store_row<NC>(orow + 2 * (int64_t)(2 * j + 1) * nk, kk, part, nn);
+                    if (j == 0) store_row<NC>(orow + 2 * (int64_t)(2 * NF) * nk, kk, part, nn);
+#pragma unroll
+                    for (int i = 0; i < NF; ++i) {
+                        const int64_t row = NB + 2 * (i * NF + j);
+                        store_row<NC>(orow + 2 * row * nk, kk, part, nn);
+                        store_row<NC>(orow + 2 * (row + 1) * nk, kk, part, nn);
+                    }
+                }
+            } else {
+                double bgv[3][NC];                    // phi_j, phi'_j, H as this thread stores them
+                if (n == ts) {
+                    // the start row is ystart[:, k] itself                rk4.py:106-107
+                    const double* ys = a.ystart;
+#pragma unroll
+                    for (int i = 0; i < NF; ++i) {
+                        const int64_t row = NB + 2 * (i * NF + j);
+#pragma unroll
+                        for (int cc = 0; cc < NC; ++cc) {
+                            x[i][cc] = ys[2 * (row * nk + kk) + part + cc];
+                            v[i][cc] = ys[2 * ((row + 1) * nk + kk) + part + cc];
+                        }
+                    }
+                    const int rows3[3] = {2 * j, 2 * j + 1, 2 * NF};
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+#pragma unroll
+                        for (int cc = 0; cc < NC; ++cc)
+                            bgv[b][cc] = ys[2 * ((int64_t)rows3[b] * nk + kk) + part + cc];
+                        if (part == 0 && a.flags) {
+                            const double ref = r[S::BG_OFF + rows3[b]];
+                            const double got = bgv[b][0];
+                            if (!(fabs(got - ref) <= 1e-9 * fabs(ref) + 1e-300))
+                                atomicOr(a.flags, PF_FLAG_BG_MISMATCH);
+                        }
+                    }
+                } else {
+                    const int rows3[3] = {2 * j, 2 * j + 1, 2 * NF};
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+                        const double val = r[S::BG_OFF + rows3[b]];
+                        if constexpr (NC == 2) { bgv[b][0] = val; bgv[b][1] = 0.0; }
+                        else { bgv[b][0] = part == 0 ? val : 0.0; }
+                    }
+                }
+                if (out) {
+                    store_row<NC>(orow + 2 * (int64_t)(2 * j) * nk, kk, part, bgv[0]);
+                    store_row<NC>(orow + 2 * (int64_t)(2 * j + 1) * nk, kk, part, bgv[1]);
+                    if (j == 0) store_row<NC>(orow + 2 * (int64_t)(2 * NF) * nk, kk, part, bgv[2]);
+#pragma unroll
+                    for (int i = 0; i < NF; ++i) {
+                        const int64_t row = NB + 2 * (i * NF + j);
+                        store_row<NC>(orow + 2 * row * nk, kk, part, x[i]);
+                        store_row<NC>(orow + 2 * (row + 1) * nk, kk, part, v[i]);
+                    }
+                }
+                if (n + 1 < a.T) {
+                    // one classical RK4 step n -> n+1                      rk4.py:27-55
+                    double kv[NF][NC], ax[NF][NC], av[NF][NC], xt[NF][NC], vt[NF][NC];
+                    mode_rhs<NF, NC>(r, kval, x, v, kv);
+#pragma unroll
+                    for (int i = 0; i < NF; ++i)
+#pragma unroll
+                        for (int cc = 0; cc < NC; ++cc) {
+                            ax[i][cc] = v[i][cc];
+                            av[i][cc] = kv[i][cc];
+                            xt[i][cc] = fma(hh, v[i][cc], x[i][cc]);
+                            vt[i][cc] = fma(hh, kv[i][cc], v[i][cc]);
+                        }
+                    mode_rhs<NF, NC>(r + SW, kval, xt, vt, kv);
+#pragma unroll
+                    for (int i = 0; i < NF; ++i)
+#pragma unroll
+                        for (int cc = 0; cc < NC; ++cc) {
+                            ax[i][cc] = fma(2.0, vt[i][cc], ax[i][cc]);
+                            av[i][cc] = fma(2.0, kv[i][cc], av[i][cc]);
+                            xt[i][cc] = fma(hh, vt[i][cc], x[i][cc]);
+                            vt[i][cc] = fma(hh, kv[i][cc], v[i][cc]);
+                        }
+                    mode_rhs<NF, NC>(r + 2 * SW, kval, xt, vt, kv);
+#pragma unroll
+                    for (int i = 0; i < NF; ++i)
+#pragma unroll
+                        for (int cc = 0; cc < NC; ++cc) {
+                            ax[i][cc] = fma(2.0, vt[i][cc], ax[i][cc]);
+                            av[i][cc] = fma(2.0, kv[i][cc], av[i][cc]);
+                            xt[i][cc] = fma(h, vt[i][cc], x[i][cc]);
+                            vt[i][cc] = fma(h, kv[i][cc], v[i][cc]);
+                        }
+                    mode_rhs<NF, NC>(r + 3 * SW, kval, xt, vt, kv);
+#pragma unroll
+                    for (int i = 0; i < NF; ++i)
+#pragma unroll
+                        for (int cc = 0; cc < NC; ++cc) {
+                            x[i][cc] = fma(h6, ax[i][cc] + vt[i][cc], x[i][cc]);
+                            v[i][cc] = fma(h6, av[i][cc] + kv[i][cc], v[i][cc]);
+                        }
+                }
+            }
+            if (out) {
+                next_out += a.out_every;
+                orow += 2 * (int64_t)NV * nk;
+            }
+        }
+        __syncthreads();                              // everyone is done reading srec[buf]
+        if (tid == 0 && c + 2 < nchunks) issue(c + 2);
+    }
+
+    if (live && a.state && ts < a.t1) {
+#pragma unroll
+        for (int i = 0; i < NF; ++i) {
+            double* sx = a.state + 2 * ((int64_t)(2 * (i * NF + j)) * nk + kk);
+            double* sv = a.state + 2 * ((int64_t)(2 * (i * NF + j) + 1) * nk + kk);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) { sx[part + c] = x[i][c]; sv[part + c] = v[i][c]; }
+        }
+    }
+}
+
+template <int NF, int NC>
+static int launch_fo(const FoArgs& a, cudaStream_t st) {
+    using S = FoShape<NF>;
+    constexpr int KPB = S::BLOCK / (3 - NC);
+    dim3 grid((unsigned)((a.nk + KPB - 1) / KPB), NF, 1);
+    fo_rk4_kernel<NF, NC><<<grid, S::BLOCK, 0, st>>>(a);
+    return 0;
+}
+
+}  // namespace pf
+
+using namespace pf;
+
+extern "C" int pf_fo_run(const pf_model* m, int64_t nk, const double* k_dev, const int64_t* tsix_dev,
+                         const double* ystart_dev, const double* rec_dev, int64_t T, double h,
+                         int64_t t0, int64_t t1, double* state_dev, double* yout_dev,
+                         int64_t out_every, int32_t* flags_dev, void* stream) {
+    int rc = check_model(m);
+    if (rc) return rc;
+    if (nk < 0 || T < 1 || t0 < 0 || t1 > T || t0 > t1 || out_every < 0) {
+        set_error("pf_fo_run: bad sizes (nk=%lld T=%lld window=[%lld,%lld) out_every=%lld)",
+                  (long long)nk, (long long)T, (long long)t0, (long long)t1, (long long)out_every);
+        return PF_E_ARG;
+    }
+    if (!(h == h) || h == 0.0) { set_error("pf_fo_run: Need to specify h."); return PF_E_STEP; }
+    if (nk == 0 || t0 == t1) return PF_OK;
+    if (!k_dev || !tsix_dev || !ystart_dev || !rec_dev) { set_error("pf_fo_run: null buffer"); return PF_E_ARG; }
+    if (t0 > 0 && !state_dev) { set_error("pf_fo_run: a window with t0 > 0 needs state_dev"); return PF_E_ARG; }
+    if (out_every > 0 && !yout_dev) { set_error("pf_fo_run: out_every > 0 needs yout_dev"); return PF_E_ARG; }
+    FoArgs a;
+    a.nk = nk; a.k = k_dev; a.tsix = tsix_dev; a.ystart = ystart_dev; a.rec = rec_dev;
+    a.T = T; a.t0 = t0; a.t1 = t1; a.state = state_dev;
+    a.yout = out_every > 0 ? yout_dev : nullptr; a.out_every = out_every; a.flags = flags_dev;
+    a.h = h;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (m->nfields) {
+        case 1: launch_fo<1, 2>(a, st); break;
+        case 2: launch_fo<2, 2>(a, st); break;
+        case 3: launch_fo<3, 1>(a, st); break;
+        case 4: launch_fo<4, 1>(a, st); break;
+        case 5: launch_fo<5, 1>(a, st); break;
+        case 6: launch_fo<6, 1>(a, st); break;
+        case 7: launch_fo<7, 1>(a, st); break;
+        case 8: launch_fo<8, 1>(a, st); break;
+        default: set_error("pf_fo_run: nfields=%d not compiled", m->nfields); return PF_E_NFIELDS;
+    }
+    PF_CUDA_CHECK(cudaGetLastError(), "pf_fo_run launch");
+    return PF_OK;
+}

@@ -1,0 +1,221 @@
+"""Device-side orchestration of the hot path: torch owns buffers and streams, the work is done
+by the hand-written kernels behind the C ABI (``include/pyflation_b200.h``).
+
+Call graph of one first-order solve (what ``rk4.rkdriver_tsix`` does in the reference,
+rk4.py:58-138, for a ``CanonicalFirstOrder.derivs``):
+
+    background_tables()   K1  pf_bg_run       serial RK4 of the shared background from column
+                                              0's start row, keeping the 4 stage arguments
+                          K1b pf_stage_table  per-step records (A, R, C) + bg row
+    first_order_device()  K2  pf_fo_run       one launch over [0, T): full trajectory in HBM
+    first_order_host()    K2  pf_fo_run       time windows into two device slabs, each copied
+                                              to (pinned) host memory while the next computes
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PfModel
+
+
+def nvar_of(nf):
+    return 2 * nf * nf + 2 * nf + 1
+
+
+def make_model(potential_func, pot_params, nfields, ainit=1.0):
+    """Resolve (name, params dict, nfields) into the C struct, with the reference's defaults
+    (cmpotentials.py) for parameters that are absent."""
+    table = _lib.potential_table()
+    if potential_func not in table:
+        raise AttributeError("module 'cmpotentials' has no attribute %r" % (potential_func,))
+    pid, nf_required, plist = table[potential_func]
+    nfields = int(nfields)
+    if nf_required and nf_required != nfields:
+        raise ValueError("potential %s is defined for nfields=%d, not %d"
+                         % (potential_func, nf_required, nfields))
+    if not 1 <= nfields <= _lib.PF_MAX_NFIELDS:
+        raise NotImplementedError("nfields=%d: kernels are compiled for 1..%d fields"
+                                  % (nfields, _lib.PF_MAX_NFIELDS))
+    m = PfModel()
+    m.potential_id = pid
+    m.nfields = nfields
+    pot_params = pot_params or {}
+    if potential_func == "nflation" and "nfields" not in pot_params:
+        raise KeyError("nfields")                       # cmpotentials.py:828
+    for i, (name, default) in enumerate(plist):
+        m.params[i] = float(pot_params.get(name, default))
+    m.ainit = float(np.asarray(ainit).reshape(-1)[0])
+    return m
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream_ptr(stream=None):
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+def require_cuda(device=None):
+    if not torch.cuda.is_available():
+        raise _lib.LibraryError("pyflation_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    return dev
+
+
+def background_tables(model, y0, T, h, simtstart=0.0, n0=0, records=True, device=None):
+    """K1 (+K1b).  Returns (bg [T, 2nf+1] f64, rec [T, REC] f64 or None) on the device."""
+    L = _lib.lib()
+    dev = require_cuda(device)
+    nf = model.nfields
+    nb = 2 * nf + 1
+    y0 = np.ascontiguousarray(np.asarray(y0, dtype=np.float64).reshape(-1))
+    if y0.shape[0] != nb:
+        raise ValueError("background start vector must have %d entries" % nb)
+    with torch.cuda.device(dev):
+        bg = torch.empty((T, nb), dtype=torch.float64, device=dev)
+        stagey = torch.empty((T, 4, nb), dtype=torch.float64, device=dev) if records else None
+        st = _stream_ptr()
+        _lib.check(L.pf_bg_run(ctypes.byref(model), T, float(h), int(n0),
+                               y0.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                               _ptr(bg), _ptr(stagey), st))
+        rec = None
+        if records:
+            rec = torch.empty((T, int(L.pf_rec_doubles(nf))), dtype=torch.float64, device=dev)
+            _lib.check(L.pf_stage_table(ctypes.byref(model), T, float(simtstart), float(h), int(n0),
+                                        _ptr(bg), _ptr(stagey), _ptr(rec), st))
+    return bg, rec
+
+
+class FirstOrderProblem(object):
+    """Inputs of one first-order solve, resident on the device."""
+
+    def __init__(self, model, k, tsix, ystart, simtstart, T, h, device=None):
+        self.dev = require_cuda(device)
+        self.model = model
+        self.nf = model.nfields
+        self.nvar = nvar_of(self.nf)
+        self.T = int(T)
+        self.h = float(h)
+        self.simtstart = float(simtstart)
+        self.nk = int(np.shape(k)[0])
+        as_dev = lambda a, dt: (a.to(self.dev, dt).contiguous() if torch.is_tensor(a)
+                                else torch.as_tensor(np.ascontiguousarray(a)).to(self.dev, dt))
+        self.k = as_dev(k, torch.float64)
+        self.tsix = as_dev(tsix, torch.int64)
+        self.ystart = as_dev(ystart, torch.complex128)
+        if tuple(self.ystart.shape) != (self.nvar, self.nk):
+            raise ValueError("ystart must have shape (%d, %d)" % (self.nvar, self.nk))
+        self.flags = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.state = torch.zeros((2 * self.nf * self.nf, self.nk), dtype=torch.complex128,
+                                 device=self.dev)
+        self.rec = None
+        self.bg = None
+
+    def build_tables(self, y0, n0):
+        self.bg, self.rec = background_tables(self.model, y0, self.T, self.h, self.simtstart,
+                                              n0, True, self.dev)
+
+    def launch(self, t0, t1, yout, out_every=1, stream=None):
+        """K2: rows [t0, t1) -> yout (device c128 tensor or None)."""
+        L = _lib.lib()
+        _lib.check(L.pf_fo_run(ctypes.byref(self.model), self.nk, _ptr(self.k), _ptr(self.tsix),
+                               _ptr(self.ystart), _ptr(self.rec), self.T, self.h, int(t0), int(t1),
+                               _ptr(self.state), _ptr(yout), int(out_every if yout is not None else 0),
+                               _ptr(self.flags), _stream_ptr(stream)))
+
+    def check_flags(self):
+        f = int(self.flags.item())
+        if f & _lib.PF_FLAG_BG_MISMATCH:
+            raise NotImplementedError(
+                "first-order start vector: the background rows of some column are not on column "
+                "0's background trajectory; the fused kernel shares one background across modes "
+                "(DESIGN.md) and there is no per-column fallback")
+
+
+def first_order_device(prob, out=None):
+    """Full trajectory kept in HBM: returns a device tensor (T, nvar, nk) complex128."""
+    with torch.cuda.device(prob.dev):
+        if out is None:
+            out = torch.empty((prob.T, prob.nvar, prob.nk), dtype=torch.complex128, device=prob.dev)
+        prob.launch(0, prob.T, out, 1)
+    return out
+
+
+def _pinned_empty(shape, dtype):
+    try:
+        return torch.empty(shape, dtype=dtype, pin_memory=True)
+    except RuntimeError:
+        return torch.empty(shape, dtype=dtype)
+
+
+def plan_window(T, nvar, nk, slab_bytes):
+    rows = int(max(1, min(T, slab_bytes // max(1, nvar * nk * 16))))
+    return rows
+
+
+def first_order_host(prob, out=None, slab_bytes=1 << 30):
+    """Trajectory delivered into host memory: time windows ping-pong between two device slabs;
+    the device->host copy of window w overlaps the integration of window w+1.
+    Returns a torch CPU tensor (T, nvar, nk) complex128 (pinned when it could be)."""
+    T, nvar, nk = prob.T, prob.nvar, prob.nk
+    if out is None:
+        out = _pinned_empty((T, nvar, nk), torch.complex128)
+    W = plan_window(T, nvar, nk, slab_bytes)
+    with torch.cuda.device(prob.dev):
+        slabs = [torch.empty((W, nvar, nk), dtype=torch.complex128, device=prob.dev)
+                 for _ in range(2 if W < T else 1)]
+        compute = torch.cuda.current_stream()
+        copier = torch.cuda.Stream()
+        copied = [None, None]
+        w = 0
+        for t0 in range(0, T, W):
+            t1 = min(T, t0 + W)
+            b = w % len(slabs)
+            if copied[b] is not None:
+                compute.wait_event(copied[b])           # slab b is free again
+            prob.launch(t0, t1, slabs[b], 1, compute)
+            done = torch.cuda.Event()
+            done.record(compute)
+            copier.wait_event(done)
+            with torch.cuda.stream(copier):
+                out[t0:t1].copy_(slabs[b][:t1 - t0], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copier)
+            copied[b] = ev
+            w += 1
+        copier.synchronize()
+        compute.synchronize()
+    return out
+
+
+def pr_spectrum_device(nf, y, k=None):
+    """K5 on rows already on the device: y (nrows, nvar, nk) c128 -> (nrows, nk) f64."""
+    L = _lib.lib()
+    nrows, nvar, nk = y.shape
+    y = y.contiguous()
+    out = torch.empty((nrows, nk), dtype=torch.float64, device=y.device)
+    with torch.cuda.device(y.device):
+        for r0 in range(0, nrows, 32768):
+            r1 = min(nrows, r0 + 32768)
+            _lib.check(L.pf_pr_spectrum(int(nf), r1 - r0, nk, _ptr(y[r0:r1]), _ptr(k),
+                                        _ptr(out[r0:r1]), _stream_ptr()))
+    return out
+
+
+def potential_eval_device(model, y):
+    """K0: (U [n], dU [n, nf], d2U [n, nf, nf]) for background vectors y [n, 2nf+1] (device)."""
+    L = _lib.lib()
+    nf = model.nfields
+    y = y.contiguous()
+    n = y.shape[0]
+    U = torch.empty(n, dtype=torch.float64, device=y.device)
+    dU = torch.empty((n, nf), dtype=torch.float64, device=y.device)
+    d2U = torch.empty((n, nf, nf), dtype=torch.float64, device=y.device)
+    with torch.cuda.device(y.device):
+        _lib.check(L.pf_potential_eval(ctypes.byref(model), n, _ptr(y), _ptr(U), _ptr(dU), _ptr(d2U),
+                                       _stream_ptr()))
+    return U, dU, d2U

@@ -1,0 +1,136 @@
+"""rk4 - drop-in for ``pyflation.rk4`` (reference rk4.py:27-144) backed by the CUDA kernels.
+
+Same names and call signatures as the reference: :func:`rkdriver_tsix`, :func:`rk4stepks`,
+:class:`SimRunError`.  A Python callable cannot cross the C ABI, so instead of calling
+``derivs`` the driver looks at the model it is bound to (``derivs.__self__``): a
+``CanonicalBackground`` goes to the background kernel, a ``CanonicalFirstOrder`` to the fused
+first-order kernel.  Any other right-hand side raises ``NotImplementedError``: there is no
+CPU fallback.
+"""
+import logging
+
+import numpy as np
+
+from .configuration import _debug
+from . import engine, _lib
+
+rk_log = logging.getLogger(__name__)
+
+
+class SimRunError(Exception):
+    """Generic error for model simulating run. (rk4.py:141)"""
+    pass
+
+
+def _number_of_steps(simtstart, tend, h):
+    # rk4.py:73 -- np.around rounds halves to even, so 0.5 -> 0 and 1.5 -> 2
+    return int(np.around((tend - simtstart) / h) + 1)
+
+
+def _bound_model(derivs):
+    from . import cosmomodels as c
+    owner = getattr(derivs, "__self__", None)
+    if isinstance(owner, c.CanonicalFirstOrder) and getattr(derivs, "__func__", None) is \
+            c.CanonicalFirstOrder.derivs:
+        return "fo", owner
+    if isinstance(owner, c.CanonicalBackground) and getattr(derivs, "__func__", None) is \
+            c.CanonicalBackground.derivs:
+        return "bg", owner
+    raise NotImplementedError(
+        "pyflation_b200.rk4 integrates CanonicalBackground.derivs and CanonicalFirstOrder.derivs "
+        "on the GPU; an arbitrary Python `derivs` (%r) cannot be run and there is no CPU "
+        "fallback." % (derivs,))
+
+
+def _check_common(tsix, simtstart, tend, h):
+    if h is None:
+        raise SimRunError("Need to specify h.")
+    tsix = np.atleast_1d(np.asarray(tsix)).astype(np.int64)
+    T = _number_of_steps(simtstart, tend, h)
+    if np.any(tsix > T):
+        raise SimRunError("Start times outside range of steps.")
+    if np.any(tsix >= T) or np.any(tsix < 0):
+        # the reference lets tsix == T through its check and then fails with an IndexError
+        # at rk4.py:107; both are reported as SimRunError here
+        raise SimRunError("Start times outside range of steps.")
+    return tsix, T
+
+
+def _xarr(simtstart, T, h):
+    return simtstart + np.arange(T) * h                     # rk4.py:78-87,134
+
+
+def rkdriver_tsix(ystart, simtstart, tsix, tend, h, derivs, yresult_host=True):
+    """Driver function for classical Runge Kutta 4th Order method.
+    Uses indexes of starting time values instead of actual times.
+    Indexes are number of steps of size h away from initial time simtstart.
+
+    Returns ``(xarr (T,), yarr (T, nvar, nk))`` laid out exactly as the reference's arrays
+    (rk4.py:95-100): rows before a mode's start index are NaN, the start row is ``ystart``.
+    """
+    kind, model = _bound_model(derivs)
+    tsix, T = _check_common(tsix, simtstart, tend, h)
+    ystart = np.asarray(ystart)
+    if ystart.ndim == 1:
+        ystart = ystart[..., np.newaxis]                    # rk4.py:93-94
+    if _debug:
+        rk_log.debug("rkdriver_tsix: %s run, T=%d, columns=%d", kind, T, ystart.shape[1])
+    try:
+        if kind == "bg":
+            yarr = _run_background(model, ystart, simtstart, tsix, T, h)
+        else:
+            yarr = _run_first_order(model, ystart, simtstart, tsix, T, h, yresult_host)
+    except _lib.ArgumentError as err:
+        raise SimRunError(str(err))
+    rk_log.info("Execution of Runge-Kutta method has finished.")
+    return _xarr(simtstart, T, h), yarr
+
+
+def _run_background(model, ystart, simtstart, tsix, T, h):
+    nf = model.nfields
+    if ystart.shape[1] != 1 or tsix.shape[0] != 1:
+        raise NotImplementedError("background runs integrate a single column")
+    if ystart.shape[0] != 2 * nf + 1:
+        raise SimRunError("background ystart must have 2*nfields+1 rows")
+    if np.iscomplexobj(ystart):
+        raise NotImplementedError("background runs are real valued")
+    pm = engine.make_model(model.potential_func, model.pot_params, nf)
+    bg, _ = engine.background_tables(pm, ystart[:, 0], T, h, simtstart, int(tsix[0]), records=False)
+    return bg.cpu().numpy().reshape(T, 2 * nf + 1, 1)
+
+
+def _run_first_order(model, ystart, simtstart, tsix, T, h, host=True):
+    nf = model.nfields
+    nvar = engine.nvar_of(nf)
+    k = np.atleast_1d(np.asarray(model.k, dtype=np.float64))
+    if ystart.shape != (nvar, k.shape[0]) or tsix.shape[0] != k.shape[0]:
+        raise SimRunError("ystart must have shape (2*nfields**2+2*nfields+1, len(k))")
+    n0 = int(tsix.min())
+    if int(tsix[0]) != n0:
+        # cosmomodels.py:641 evaluates the potential on column 0 only: in the reference every
+        # column that starts before column 0 is poisoned to NaN for the whole run
+        raise SimRunError("column 0 must be the earliest-starting mode (k ascending): the "
+                          "potential is evaluated on column 0 (cosmomodels.py:641)")
+    pm = engine.make_model(model.potential_func, model.pot_params, nf, model.ainit)
+    prob = engine.FirstOrderProblem(pm, k, tsix, ystart.astype(np.complex128, copy=False),
+                                    simtstart, T, h)
+    prob.build_tables(np.real(ystart[0:2 * nf + 1, 0]), n0)
+    if host:
+        out = engine.first_order_host(prob).numpy()
+    else:
+        out = engine.first_order_device(prob)
+    prob.check_flags()
+    return out
+
+
+def rk4stepks(x, y, h, dydx, dargs, derivs):
+    '''Do one step of the classical 4th order Runge Kutta method,
+    starting from y at x with time step h and derivatives given by derivs.
+
+    Runs as a two-row solve on the device; ``dydx`` is recomputed there, so it is ignored.'''
+    y = np.asarray(y)
+    single = y.ndim == 1
+    ncol = 1 if single else y.shape[1]
+    _, yarr = rkdriver_tsix(y, x, np.zeros(ncol, dtype=np.int64), x + h, h, derivs)
+    out = yarr[1]
+    return out[:, 0] if single else out
