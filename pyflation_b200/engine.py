@@ -136,12 +136,14 @@ class FirstOrderProblem(object):
                 "(DESIGN.md) and there is no per-column fallback")
 
 
-def first_order_device(prob, out=None):
-    """Full trajectory kept in HBM: returns a device tensor (T, nvar, nk) complex128."""
+def first_order_device(prob, out=None, out_every=1):
+    """Trajectory kept in HBM: returns a device tensor (ceil(T/out_every), nvar, nk) complex128
+    holding rows 0, out_every, 2*out_every, ... (out_every=1: the full trajectory)."""
     with torch.cuda.device(prob.dev):
+        nrows = (prob.T + out_every - 1) // out_every
         if out is None:
-            out = torch.empty((prob.T, prob.nvar, prob.nk), dtype=torch.complex128, device=prob.dev)
-        prob.launch(0, prob.T, out, 1)
+            out = torch.empty((nrows, prob.nvar, prob.nk), dtype=torch.complex128, device=prob.dev)
+        prob.launch(0, prob.T, out, out_every)
     return out
 
 

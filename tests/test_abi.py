@@ -1,0 +1,95 @@
+"""The C-ABI library builds, loads, and exports exactly what include/pyflation_b200.h declares
+(no compute calls here: this file runs without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "pyflation_b200.h")
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pyflation_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    names = header_functions()
+    assert len(names) >= 17
+    for name in names:
+        assert hasattr(L, name), "missing export %s" % name
+    assert sorted(_lib.EXPORTS) == names
+    assert _lib.lib().pf_version() == 1
+
+
+def test_potential_table_matches_reference_defaults(oracle):
+    """Names, field counts and parameter defaults of the device potentials agree with the
+    oracle's restatement of cmpotentials.py (itself pinned to the reference)."""
+    from pyflation_b200 import _lib, cmpotentials
+    table = _lib.potential_table()
+    assert set(table) == set(oracle.POTENTIALS)
+    assert [n for n, v in sorted(table.items(), key=lambda kv: kv[1][0])][:3] == \
+        ["msqphisq", "lambdaphi4", "linde"]
+    y1 = np.array([17.3, -0.1, 1e-5])
+    y2 = np.array([11.0, -0.1, 0.7, 0.02, 1e-5])
+    for name, (pid, nf, plist) in table.items():
+        assert nf in (0, 1, 2)
+        # defaults: perturbing each library default must be visible through the oracle
+        y = y1 if nf == 1 else y2
+        base = {"nfields": 2} if name == "nflation" else None
+        U0 = oracle.POTENTIALS[name](y, base)[0]
+        explicit = dict(base or {})
+        explicit.update({p: d for p, d in plist})
+        assert oracle.POTENTIALS[name](y, explicit)[0] == U0, name
+        # and the host-side drop-in module agrees with the oracle
+        got = getattr(cmpotentials, name)(y, base)
+        want = oracle.POTENTIALS[name](y, base)
+        assert got[0] == pytest.approx(want[0], rel=1e-15)
+        np.testing.assert_allclose(got[1], want[1], rtol=1e-15)
+        np.testing.assert_allclose(got[2], want[2], rtol=1e-15)
+        if want[3] is None:
+            assert got[3] is None
+        else:
+            np.testing.assert_allclose(got[3], want[3], rtol=1e-15, atol=0)
+            assert np.shape(got[3]) == np.shape(want[3])
+
+
+def test_sizes_and_step_count():
+    from pyflation_b200 import _lib
+    L = _lib.lib()
+    assert [L.pf_nvar(n) for n in (1, 2, 8)] == [5, 13, 145]
+    assert [L.pf_rec_doubles(n) for n in (1, 2, 8)] == [16, 30, 282]
+    # rk4.py:73: int(around((tend - simtstart)/h) + 1), halves to even
+    for tend, h in ((83.0, 0.01), (81.63292929292929, 0.01), (0.025, 0.01), (0.035, 0.01), (1.0, 0.3)):
+        assert L.pf_number_of_steps(0.0, tend, h) == int(np.around(tend / h) + 1)
+
+
+def test_argument_errors_without_gpu():
+    """Argument validation happens before any CUDA call, so it is testable on a CPU box."""
+    from pyflation_b200 import _lib, engine
+    L = _lib.lib()
+    m = engine.make_model("msqphisq", {}, 1)
+    y0 = (ctypes.c_double * 3)(18.0, -0.1, 1e-5)
+    assert L.pf_bg_run(ctypes.byref(m), 10, float("nan"), 0, y0, 1, 0, None) == -4   # PF_E_STEP
+    assert b"Need to specify h" in L.pf_last_error()
+    assert L.pf_bg_run(ctypes.byref(m), 10, 0.01, 11, y0, 1, 0, None) == -5          # PF_E_START
+    m.nfields = 2
+    assert L.pf_bg_run(ctypes.byref(m), 10, 0.01, 0, y0, 1, 0, None) == -2           # PF_E_POTENTIAL
+    m.nfields = 9
+    assert L.pf_bg_run(ctypes.byref(m), 10, 0.01, 0, y0, 1, 0, None) == -3           # PF_E_NFIELDS
+    with pytest.raises(AttributeError):
+        engine.make_model("nosuchpotential", {}, 1)
+    with pytest.raises(KeyError):
+        engine.make_model("nflation", {}, 2)                                          # cmpotentials.py:828
+    with pytest.raises(ValueError):
+        engine.make_model("hybridquadratic", {}, 1)

@@ -1,0 +1,345 @@
+"""Parity of the CUDA path with the reference (golden vectors) and the oracle -- B200 only.
+
+Tolerance: 1e-9 relative (BASELINE.json north_star) on background rows, perturbation
+amplitudes and P_R; start rows and NaN prefixes must be exact.  Everything goes through the
+drop-in Python API, which itself calls the C ABI (ctypes) -- there is no other path.
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, fo_fixture_names, load_fo, model_kwargs, rel_err, mode_rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9                      # north-star tolerance
+CONDITIONING = json.load(open(os.path.join(GOLDEN, "conditioning.json")))
+KMIN, KMAX = 0.85e-60, 8.2165e-58
+
+
+def run_model(g):
+    from pyflation_b200 import cosmomodels as c
+    m = getattr(c, g["cls"])(**model_kwargs(g))
+    m.run(saveresults=False)
+    return m
+
+
+def tolerances(name):
+    """1e-9 unless the reference's own computation is ill-conditioned for this fixture
+    (tests/golden/make_conditioning.py: response of the oracle to a 1-ulp input change)."""
+    c = CONDITIONING[name]
+    return (max(TOL, 100 * c["bg"]), max(TOL, 100 * c["amp"]), max(TOL, 100 * c["phase"]))
+
+
+def phase_normalised(y, y0, nf):
+    """Divide column j of every mode matrix by the phase of its own start value dphi_jj: the
+    linear system maps a global phase of the start vector onto the whole trajectory, and the
+    Bunch-Davies phase k*(eta_* - eta_init) ~ 1e8..1e11 rad is not reproducible to 1e-9
+    between libm builds (conditioning.json, column "phase")."""
+    nb = 2 * nf + 1
+    out = y.copy()
+    for j in range(nf):
+        d = y0[nb + 2 * (j * nf + j)]
+        u = np.where(np.abs(d) > 0, d / np.where(np.abs(d) > 0, np.abs(d), 1), 1.0)
+        for i in range(nf):
+            r = nb + 2 * (i * nf + j)
+            out[:, r] = y[:, r] * np.conj(u)
+            out[:, r + 1] = y[:, r + 1] * np.conj(u)
+    return out
+
+
+@pytest.mark.parametrize("name", fo_fixture_names())
+def test_first_order_stage_matches_reference_golden(name):
+    """THE hot path: rk4.rkdriver_tsix on CanonicalFirstOrder.derivs, fed the reference's own
+    start vectors / start rows / ainit (cosmomodels.py:1376-1404), raw complex comparison."""
+    from pyflation_b200 import cosmomodels as c
+    g = load_fo(name)
+    nf = g["nfields"]
+    tol_bg, _, _ = tolerances(name)
+    fo = c.CanonicalFirstOrder(ystart=g["foystart"].copy(), tstart=g["fotstart"], simtstart=0.0,
+                               tstartindex=g["fotstartindex"], tend=float(g["fotend"]),
+                               tstep_wanted=0.01, solver="rkdriver_tsix", k=g["k"],
+                               ainit=g["ainit"], potential_func=g["potential"],
+                               pot_params=dict(g["params"]), nfields=nf)
+    fo.run(saveresults=False)
+    assert fo.yresult.shape == (g["T"], 2 * nf * nf + 2 * nf + 1, len(g["k"]))
+    assert fo.yresult.dtype == np.complex128 and fo.yresult.flags["C_CONTIGUOUS"]
+    assert rel_err(fo.tresult, g["tresult"]) == 0.0
+    rows = g["rows"]
+    got, want = fo.yresult[rows], g["yrows"]
+    assert rel_err(got[:, :2 * nf + 1], want[:, :2 * nf + 1]) < tol_bg
+    assert mode_rel_err(got, want, nf) < tol_bg
+    # start rows are ystart itself, bit for bit; rows before them are NaN+NaNj
+    for col, s in enumerate(g["fotstartindex"]):
+        assert np.array_equal(fo.yresult[s, :, col], g["foystart"][:, col])
+        assert np.isnan(fo.yresult[:s, :, col].real).all() and np.isnan(fo.yresult[:s, :, col].imag).all()
+        assert not np.isnan(fo.yresult[s:, 2 * nf + 1:, col]).any()
+    # final curvature power spectrum through the drop-in analysis module
+    fo.tresult, fo.k = fo.tresult, g["k"]
+    from pyflation_b200.analysis import adiabatic
+    assert rel_err(adiabatic.Pr(fo, tix=-1), g["Pr_last"]) < tol_bg
+    assert rel_err(adiabatic.scaled_Pr(fo, tix=-1), g["scaled_Pr_last"]) < tol_bg
+    assert rel_err(adiabatic.Pr(fo)[rows], g["Pr_rows"]) < tol_bg
+
+
+@pytest.mark.parametrize("name", fo_fixture_names())
+def test_full_two_stage_run_matches_reference_golden(name):
+    """FOCanonicalTwoStage(...).run(): background kernel -> host IC glue -> first-order kernel."""
+    g = load_fo(name)
+    m = run_model(g)
+    nf = g["nfields"]
+    tol_bg, tol_amp, tol_phase = tolerances(name)
+    assert m.yresult.shape == (g["T"], 2 * nf * nf + 2 * nf + 1, len(g["k"]))
+    assert m.fotendindex == int(g["fotendindex"]) and m.fotend == float(g["fotend"])
+    assert np.array_equal(m.fotstartindex, g["fotstartindex"])
+    assert rel_err(np.asarray(m.ainit, float).reshape(-1), g["ainit"].reshape(-1)) < tol_bg
+    # background rows up to the end of inflation: nothing reads later rows, and for some
+    # fixtures (inflection: omega*h > 2.8 after inflation) RK4 itself is unstable there
+    infl = g["bgrows"] <= int(g["fotendindex"])
+    assert rel_err(m.bgmodel.yresult[g["bgrows"][infl]], g["bgyrows"][infl]) < tol_bg
+    nb = 2 * nf + 1
+    assert rel_err(m.foystart[:nb], g["foystart"][:nb]) < tol_bg
+    assert rel_err(np.abs(m.foystart[nb:]), np.abs(g["foystart"][nb:]), 1e-200) < tol_amp
+    assert rel_err(m.foystart[nb:], g["foystart"][nb:], 1e-200) < tol_phase
+    assert rel_err(m.tresult, g["tresult"]) == 0.0
+    rows = g["rows"]
+    got = phase_normalised(m.yresult[rows], m.foystart, nf)
+    want = phase_normalised(g["yrows"], g["foystart"], nf)
+    assert rel_err(got[:, :nb], want[:, :nb]) < tol_bg
+    assert mode_rel_err(got, want, nf) < tol_bg
+    for col, s in enumerate(m.fotstartindex):
+        assert np.array_equal(m.yresult[s, :, col], m.foystart[:, col])
+        assert np.isnan(m.yresult[:s, :, col].real).all()
+    assert rel_err(m.Pr[-1:], g["Pr_last"]) < tol_bg
+    assert rel_err(m.scaled_Pr[-1:], g["scaled_Pr_last"]) < tol_bg
+    assert rel_err(m.Pr[rows], g["Pr_rows"]) < tol_bg
+
+
+def _problem(g, m=None, k=None):
+    """Device problem for golden fixture g (bg + ICs through the package)."""
+    from pyflation_b200 import cosmomodels as c, engine
+    kw = model_kwargs(g)
+    if k is not None:
+        kw["k"] = k
+    m = getattr(c, g["cls"])(**kw)
+    m.runbg()
+    m.setfoics()
+    T = int(np.around((m.fotend - m.simtstart) / m.tstep_wanted) + 1)
+    pm = engine.make_model(m.potential_func, m.pot_params, m.nfields, m.ainit)
+    prob = engine.FirstOrderProblem(pm, m.k, m.fotstartindex, m.foystart, m.simtstart, T, m.tstep_wanted)
+    prob.build_tables(np.real(m.foystart[0:2 * m.nfields + 1, 0]), int(m.fotstartindex.min()))
+    return m, prob
+
+
+@pytest.mark.parametrize("name,nk,every", [
+    ("c1_msqphisq_k4", "K4", 1),                 # BASELINE config 1: 2053 modes, full trajectory
+    ("c2_lambdaphi4_2p16", 2 ** 16, 1),          # config 2: 2^16 modes, full trajectory (41 GB)
+    ("c3_hybridquadratic_2p20", 2 ** 20, 40),    # config 3: every 40th row (full = 1.6 TB)
+    ("c4_nflation8_2p18", 2 ** 18, 100),         # config 4: every 100th row (full = 5 TB)
+    ("c5_msqphisq_2p20", 2 ** 20, 40),           # config 5, one GPU's worth
+])
+def test_baseline_sizes_against_golden_columns(name, nk, every):
+    """At BASELINE.json's full sizes the oracle cannot run, but columns are independent: the
+    golden files hold columns ``kix`` of exactly these grids, computed by the reference."""
+    import torch
+    from pyflation_b200 import engine, helpers
+    g = load_fo(name)
+    if nk == "K4":
+        k = helpers.seq(KMIN, helpers.getkend(0.85e-60, 0.4e-60, 1025), 0.4e-60)
+    else:
+        k = np.linspace(KMIN, KMAX, nk)
+    assert np.array_equal(k[g["kix"]], g["k"])
+    m, prob = _problem(g, k=k)
+    assert prob.T == g["T"]
+    assert np.array_equal(m.fotstartindex[g["kix"]], g["fotstartindex"])
+    out = engine.first_order_device(prob, out_every=every)
+    prob.check_flags()
+    torch.cuda.synchronize()
+    cols = torch.as_tensor(g["kix"], device=out.device)
+    sel = g["rows"][g["rows"] % every == 0]
+    got = out[torch.as_tensor(sel // every, device=out.device)][:, :, cols].cpu().numpy()
+    want = g["yrows"][np.isin(g["rows"], sel)]
+    nf = g["nfields"]
+    got = phase_normalised(got, m.foystart[:, g["kix"]], nf)
+    want = phase_normalised(want, g["foystart"], nf)
+    assert rel_err(got[:, :2 * nf + 1], want[:, :2 * nf + 1]) < TOL
+    assert mode_rel_err(got, want, nf) < TOL
+    # final P_R(k) on the device (K5) for the golden columns
+    last = (prob.T - 1) // every
+    if (prob.T - 1) % every == 0:
+        pr = engine.pr_spectrum_device(nf, out[last:last + 1])[:, cols].cpu().numpy()
+        assert rel_err(pr, g["Pr_last"]) < TOL
+    # size-independent properties on the whole batch: NaN prefix / started rows per column
+    started = torch.as_tensor(m.fotstartindex, device=out.device)
+    rowid = torch.arange(out.shape[0], device=out.device) * every
+    nan_re = torch.isnan(out[:, 2 * nf + 1].real)
+    assert torch.equal(nan_re, rowid[:, None] < started[None, :])
+    del out
+
+
+def test_windowed_host_path_is_bitwise_identical():
+    """Time windows + state carry + pipelined D2H give the same bits as one launch."""
+    import torch
+    from pyflation_b200 import engine
+    g = load_fo("c3_hybridquadratic_2p20")
+    m, prob = _problem(g, k=np.linspace(KMIN, KMAX, 333))
+    full = engine.first_order_device(prob).cpu().numpy()
+    for slab in (1 << 20, 7 << 20):            # ~15 and ~100 rows per window
+        prob.state.zero_()
+        host = engine.first_order_host(prob, slab_bytes=slab).numpy()
+        assert np.array_equal(host.view(np.float64), full.view(np.float64), equal_nan=True)
+    every = engine.first_order_device(prob, out_every=7).cpu().numpy()
+    assert np.array_equal(every.view(np.float64), full[::7].view(np.float64), equal_nan=True)
+
+
+def test_linearity_and_column_independence():
+    """The perturbation equations are linear with real coefficients: scaling a column's start
+    vector by 4 (exact in binary) scales its trajectory by 4 bit-for-bit; a column's result
+    does not depend on which other columns are in the batch."""
+    import torch
+    from pyflation_b200 import engine
+    g = load_fo("c1_msqphisq_k4")
+    m, prob = _problem(g)
+    base = engine.first_order_device(prob).cpu().numpy()
+    nb = 3
+    y2 = m.foystart.copy()
+    y2[nb:, 1::2] *= 4.0
+    y2[nb:, 2::4] *= 1j                              # rotate some columns by i as well
+    pm = engine.make_model(m.potential_func, m.pot_params, 1, m.ainit)
+    prob2 = engine.FirstOrderProblem(pm, m.k, m.fotstartindex, y2, 0.0, prob.T, 0.01)
+    prob2.build_tables(np.real(y2[0:nb, 0]), int(m.fotstartindex.min()))
+    scaled = engine.first_order_device(prob2).cpu().numpy()
+    fac = np.ones(len(m.k), dtype=complex)
+    fac[1::2] *= 4.0
+    fac[2::4] *= 1j
+    assert np.array_equal((base[:, nb:] * fac).view(np.float64), scaled[:, nb:].view(np.float64), equal_nan=True)
+    # sub-batch: columns 0, 5, 6, 20
+    pick = np.array([0, 5, 6, 20])
+    prob3 = engine.FirstOrderProblem(pm, m.k[pick], m.fotstartindex[pick], m.foystart[:, pick], 0.0, prob.T, 0.01)
+    prob3.build_tables(np.real(m.foystart[0:nb, 0]), int(m.fotstartindex.min()))
+    sub = engine.first_order_device(prob3).cpu().numpy()
+    assert np.array_equal(sub.view(np.float64), np.ascontiguousarray(base[:, :, pick]).view(np.float64), equal_nan=True)
+
+
+def test_edge_cases_and_errors():
+    import torch
+    from pyflation_b200 import cosmomodels as c, rk4, engine, helpers
+    g = load_fo("c1_msqphisq_k4")
+    # single mode, and batches whose size is not a multiple of the warp / block size
+    for nk in (1, 31):
+        gg = dict(g)
+        gg["k"] = g["k"][:nk]
+        m = run_model(gg)
+        assert rel_err(m.yresult[g["rows"]][:, :3], g["yrows"][:, :3, :nk]) < TOL
+        assert mode_rel_err(m.yresult[g["rows"]], g["yrows"][:, :, :nk], 1) < TOL
+    gg = dict(g)
+    gg["k"] = helpers.seq(KMIN, helpers.getkend(0.85e-60, 0.4e-60, 1025), 0.4e-60)[:129]
+    m = run_model(gg)                                   # 129 modes: golden holds 0, 64, 128
+    assert np.array_equal(gg["k"][[0, 64, 128]], g["k"][:3])
+    assert mode_rel_err(m.yresult[g["rows"]][:, :, [0, 64, 128]], g["yrows"][:, :, :3], 1) < TOL
+    # empty batch through the C ABI: nothing to do, no error
+    m, prob = _problem(g)
+    from pyflation_b200 import _lib
+    assert _lib.lib().pf_fo_run(ctypes.byref(prob.model), 0, None, None, None, None, prob.T, 0.01, 0, prob.T,
+                                None, None, 0, None, None) == 0
+    # column 0 must start first (the reference NaN-poisons such runs, cosmomodels.py:641)
+    fo = c.CanonicalFirstOrder(k=m.k[::-1].copy(), ainit=m.ainit, ystart=m.foystart[:, ::-1].copy(),
+                               tstartindex=m.fotstartindex[::-1].copy(), tend=m.fotend,
+                               potential_func="msqphisq", pot_params={"nfields": 1})
+    with pytest.raises(rk4.SimRunError):
+        fo.run(saveresults=False)
+    # unsorted start rows after column 0 are fine
+    perm = np.concatenate([[0], np.arange(len(m.k) - 1, 0, -1)])
+    fo = c.CanonicalFirstOrder(k=m.k[perm], ainit=m.ainit, ystart=m.foystart[:, perm].copy(),
+                               tstartindex=m.fotstartindex[perm], tend=m.fotend,
+                               potential_func="msqphisq", pot_params={"nfields": 1})
+    fo.run(saveresults=False)
+    assert rel_err(fo.yresult[g["rows"]][:, :, np.argsort(perm)][:, :3], g["yrows"][:, :3]) < TOL
+    assert mode_rel_err(fo.yresult[g["rows"]][:, :, np.argsort(perm)], g["yrows"], 1) < TOL
+    # a column whose background rows are off column 0's trajectory is refused, not mis-computed
+    bad = m.foystart.copy()
+    bad[0, 7] *= 1.001
+    fo = c.CanonicalFirstOrder(k=m.k, ainit=m.ainit, ystart=bad, tstartindex=m.fotstartindex,
+                               tend=m.fotend, potential_func="msqphisq", pot_params={"nfields": 1})
+    with pytest.raises(NotImplementedError):
+        fo.run(saveresults=False)
+    # start index outside the step range (rk4.py:74)
+    fo = c.CanonicalFirstOrder(k=m.k, ainit=m.ainit, ystart=m.foystart, tstartindex=m.fotstartindex + 9000,
+                               tend=m.fotend, potential_func="msqphisq", pot_params={"nfields": 1})
+    with pytest.raises(rk4.SimRunError):
+        fo.run(saveresults=False)
+    # inflation that never ends (run_config's msqphisq_withV0 fixture): ModelError, as the reference
+    mv = c.FOCanonicalTwoStage(k=g["k"], potential_func="msqphisq_withV0", pot_params={"nfields": 1},
+                               nfields=1, bgystart=np.array([18.0, 0.0, 0.0]))
+    with pytest.raises(c.ModelError):
+        mv.run(saveresults=False)
+
+
+def test_rk4stepks_single_step():
+    """rk4.rk4stepks (rk4.py:27-55) == row tsix+1 of the driver's output."""
+    from pyflation_b200 import cosmomodels as c, rk4
+    g = load_fo("c1_msqphisq_k4")
+    m = run_model(g)
+    s = int(m.fotstartindex.max())
+    fo = m.firstordermodel
+    y = m.yresult[s]
+    out = rk4.rk4stepks(m.tresult[s], y, 0.01, None, {}, fo.derivs)
+    assert rel_err(out[:3], m.yresult[s + 1][:3]) < 1e-12
+    assert rel_err(out[3:], m.yresult[s + 1][3:]) < 1e-9
+
+
+def test_device_potentials_match_reference():
+    """All 18 device potentials (U, dU, d2U) at the golden points computed by the reference."""
+    import torch
+    from pyflation_b200 import engine
+    g = np.load(os.path.join(GOLDEN, "potentials.npz"))
+    tags = sorted(set(key.rsplit("_", 1)[0] for key in g.files if key.endswith("_y")))
+    custom = {"msqphisq__custom": {"mass": 1e-5}, "lambdaphi4__custom": {"lambda": 2e-13},
+              "step_potential__custom": {"mass": 6e-6, "c": 0.002, "d": 0.03, "phi_s": 14.8},
+              "hybridquadratic__custom": {"m1": 2e-6, "m2": 8e-6},
+              "nflation__custom": {"nfields": 2, "mass": 1e-6}}
+    seen = set()
+    for tag in tags:
+        name, variant = tag.split("__")
+        if variant == "complex":
+            continue
+        params = dict(custom.get(tag, {}))
+        y = np.real(g[tag + "_y"]).astype(np.float64)
+        nf = (y.shape[1] - 1) // 2
+        if name == "nflation":
+            params["nfields"] = nf
+        pm = engine.make_model(name, params, nf)
+        U, dU, d2U = engine.potential_eval_device(pm, torch.as_tensor(y, device="cuda"))
+        assert rel_err(U.cpu().numpy(), np.real(g[tag + "_U"])) < 1e-13, tag
+        assert rel_err(dU.cpu().numpy(), np.real(g[tag + "_dU"]).reshape(len(y), nf), 1e-200) < 1e-12, tag
+        assert rel_err(d2U.cpu().numpy(), np.real(g[tag + "_d2U"]).reshape(len(y), nf, nf), 1e-200) < 1e-12, tag
+        seen.add(name)
+    assert len(seen) == 18
+
+
+def test_pr_kernel_known_answers():
+    """K5 against the reference's hand-computed P_R vectors (test_adiabatic.py:155-260)."""
+    import torch
+    from pyflation_b200 import engine
+    g = np.load(os.path.join(GOLDEN, "kat_adiabatic.npz"))
+
+    def pack(phidot, modes, nf):
+        lent, nk = modes.shape[0], modes.shape[-1]
+        y = np.zeros((lent, 2 * nf * nf + 2 * nf + 1, nk), dtype=np.complex128)
+        y[:, 2 * nf + 1::2] = modes.reshape(lent, nf * nf, nk)
+        y[:, 1:2 * nf:2] = phidot
+        return torch.as_tensor(y, device="cuda")
+
+    pr = engine.pr_spectrum_device(2, pack(g["two_real_phidot"], g["two_real_modes"], 2)).cpu().numpy()
+    np.testing.assert_allclose(pr, [[4981 / 16900.0]], rtol=1e-14)
+    pr = engine.pr_spectrum_device(2, pack(g["two_complex_phidot"], g["two_complex_modes"], 2)).cpu().numpy()
+    np.testing.assert_allclose(pr, [[11 / 4.0]], rtol=1e-14)
+    pr = engine.pr_spectrum_device(1, pack(np.array([[[1.7]]]), np.array([[[[7.0]]]]), 1)).cpu().numpy()
+    np.testing.assert_allclose(pr, [[49 / 1.7 ** 2]], rtol=1e-14)
+    y = pack(g["block_phidot"], g["block_modes"], 3)
+    np.testing.assert_allclose(engine.pr_spectrum_device(3, y).cpu().numpy(), g["block_Pr"], rtol=1e-13)
+    k = torch.as_tensor(np.array([1e-60, 5.25e-60]), device="cuda")
+    np.testing.assert_allclose(engine.pr_spectrum_device(3, y, k).cpu().numpy(),
+                               g["block_Pr"] * (k.cpu().numpy() ** 3 / (2 * np.pi ** 2)), rtol=1e-13)

@@ -1,0 +1,159 @@
+"""Host-side glue of the drop-in package (no GPU): argument checking, vectorised horizon
+crossing, Bunch-Davies initial conditions, analysis functions, loud failure without CUDA."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_fo, model_kwargs, rel_err
+
+
+class _FakeBg(object):
+    """A finished background run, injected the way the reference's tests inject yresult
+    (analysis/test/test_adiabatic.py:138-144)."""
+
+    def __init__(self, t, y, nf):
+        self.tresult, self.yresult = t, y
+        self.phidots_ix = slice(1, 2 * nf, 2)
+
+    def getepsilon(self):
+        return 0.5 * np.sum(self.yresult[:, self.phidots_ix, 0] ** 2, axis=1)
+
+
+def make_model(g):
+    from pyflation_b200 import cosmomodels as c
+    return getattr(c, g["cls"])(**model_kwargs(g))
+
+
+@pytest.mark.parametrize("name", ["c1_msqphisq_k4", "c3_hybridquadratic_2p20", "ic_nophase",
+                                  "ic_suppress", "ic_fixedainit", "hilltopaxion"])
+def test_initial_conditions_match_reference(oracle, name):
+    g = load_fo(name)
+    m = make_model(g)
+    nf = g["nfields"]
+    bgt, bgy = oracle.run_background(g["potential"], g["params"], nf, g["bgystart"].copy())
+    m.bgmodel = _FakeBg(bgt, bgy, nf)
+    m.bgmodel.epsilon = m.bgmodel.getepsilon()
+    m.fotend, m.fotendindex = oracle.find_inflation_end(bgt, m.bgmodel.epsilon)
+    m.setfoics()
+    assert np.array_equal(m.fotstartindex, g["fotstartindex"])
+    assert rel_err(m.fotstart, g["fotstart"]) == 0.0
+    assert rel_err(np.asarray(m.ainit, dtype=float).reshape(-1), g["ainit"].reshape(-1)) < 1e-15
+    assert rel_err(np.asarray(m.etainit).reshape(-1), g["etainit"].reshape(-1)) < 1e-15
+    assert rel_err(m.foystart, g["foystart"]) < 1e-14
+    assert m.foystart.dtype == np.complex128 and m.foystart.shape == g["foystart"].shape
+
+
+def test_vectorised_crossing_equals_reference_loop(oracle):
+    """searchsorted on the running maximum == the reference's per-mode np.where scan
+    (cosmomodels.py:1108), including a non-monotone a*H."""
+    from pyflation_b200 import cosmomodels as c
+    rng = np.random.RandomState(5)
+    t = np.arange(600) * 0.01
+    H = 1e-5 * (1 + 0.3 * np.sin(40 * t)) * np.exp(-0.02 * t)     # wiggly: a*H not monotone
+    m = c.FOCanonicalTwoStage(k=np.array([1.0]), nfields=1)
+    m.ainit = 3e-3
+    aH = m.ainit * np.exp(t) * H
+    assert np.any(np.diff(aH) < 0)
+    k = np.sort(rng.uniform(50 * aH[3], 50 * aH.max() * 0.999, 257))
+    m.k = k
+    want_rows, want_t = oracle.crossing_indices(k, t, H, m.ainit, 50)
+    got = m.findallkcrossings(t, H[:, None])
+    assert np.array_equal(got[:, 0].astype(int), want_rows)
+    assert np.array_equal(got[:, 1], want_t)
+    row, efold = m.findkcrossing(k[17], t, H)
+    assert row == want_rows[17] and efold == want_t[17]
+    m.k = np.array([50 * aH.max() * 1.01])
+    with pytest.raises(c.ModelError):
+        m.findallkcrossings(t, H)
+
+
+def test_constructor_validation_matches_reference():
+    from pyflation_b200 import cosmomodels as c
+    with pytest.raises(ValueError):
+        c.CosmologicalModel(tstart=5.0, tend=5.0)
+    with pytest.raises(ValueError):
+        c.CosmologicalModel(tstart=6.0, tend=5.0)
+    with pytest.raises(ValueError):
+        c.CosmologicalModel(solver="euler")
+    with pytest.raises(ValueError):
+        c.CosmologicalModel(nfields=0)
+    with pytest.raises(c.ModelError):
+        c.CosmologicalModel(pot_params=[1, 2])
+    with pytest.raises(AttributeError):
+        c.CosmologicalModel(potential_func="nosuchpotential")
+    m = c.FOCanonicalTwoStage(nfields=2, potential_func="hybridquadratic")
+    assert m.ystart.shape == (2 * 4 + 4 + 1,) and m.cq == 50
+    assert (m.H_ix, m.bg_ix, m.dps_ix, m.dpdots_ix) == (4, slice(0, 5), slice(5, None, 2), slice(6, None, 2))
+    np.testing.assert_allclose(m.bgystart, [18 / np.sqrt(2), -0.1 / np.sqrt(2)] * 2 + [0.0])
+    bg = c.CanonicalBackground(ystart=np.array([18.0, -0.1, 0.0]), potential_func="msqphisq")
+    U = 0.5 * 6.3267e-6 ** 2 * 18.0 ** 2
+    assert bg.ystart[2] == pytest.approx(np.sqrt(U / (3 - 0.5 * 0.01)), rel=1e-15)   # findH
+
+
+def test_analysis_known_answers():
+    """The reference's own P_R tests (analysis/test/test_adiabatic.py:126-260) against the
+    drop-in analysis module, model built and injected exactly as those tests do."""
+    from pyflation_b200 import cosmomodels as c
+    from pyflation_b200.analysis import adiabatic, utilities
+    g = np.load(os.path.join(GOLDEN, "kat_adiabatic.npz"))
+
+    def getmodel(phidot, modes, k, lent, nfields, axis):
+        m = c.FOCanonicalTwoStage(k=k, nfields=nfields)
+        m.yresult = np.zeros((lent, 2 * nfields + 1 + 2 * nfields ** 2, len(k)), dtype=np.complex128)
+        m.yresult[:, m.dps_ix] = utilities.flattenmodematrix(modes, nfields, ix1=axis, ix2=axis + 1)
+        m.yresult[:, m.phidots_ix] = phidot
+        m.tresult = np.arange(lent) * 0.01
+        return m
+
+    k1 = np.array([5.25e-60])
+    m = getmodel(np.array([7, 9]).reshape((1, 2, 1)), np.array([[1, 3], [2, 5]]).reshape((1, 2, 2, 1)), k1, 1, 2, 1)
+    np.testing.assert_almost_equal(adiabatic.Pr(m), [[4981 / 16900.0]])
+    m = getmodel(np.array([1, 1]).reshape((1, 2, 1)), np.array([[1, 1j], [-1j, 3 - 1j]]).reshape((1, 2, 2, 1)), k1, 1, 2, 1)
+    arr = adiabatic.Pr(m)
+    np.testing.assert_almost_equal(arr, [[11 / 4.0]])
+    assert not np.iscomplexobj(arr)
+    m = getmodel(1.7, np.array([[[7]]]), k1, 1, 1, 0)
+    np.testing.assert_almost_equal(adiabatic.Pr(m), [[49 / 1.7 ** 2]])
+    np.testing.assert_almost_equal(adiabatic.scaled_Pr(m), [[49 / 1.7 ** 2 * k1[0] ** 3 / (2 * np.pi ** 2)]])
+    # block case: shapes and values against the reference's functions
+    modes, phidot = g["block_modes"], g["block_phidot"]
+    np.testing.assert_allclose(adiabatic.Pr_spectrum(phidot, modes, 1), g["block_Pr"], rtol=1e-14)
+    np.testing.assert_allclose(adiabatic.Pphi_matrix(modes, 1), g["block_Pphi"], rtol=1e-14)
+    assert adiabatic.Pphi_matrix(modes, 1).shape == modes.shape
+    m = getmodel(np.arange(24.0).reshape((4, 3, 2)), np.arange(72.0).reshape((4, 3, 3, 2)),
+                 np.array([1e-60, 5.25e-60]), 4, 3, 1)
+    assert adiabatic.Pr(m).shape == (4, 2)
+    assert adiabatic.Pr(m, tix=-1, kix=1).shape == (1, 1)
+    np.testing.assert_allclose(utilities.kscaling(g["kscaling_k"]), g["kscaling"], rtol=1e-15)
+    with pytest.raises(ValueError):
+        utilities.getmodematrix(np.zeros((2, 5, 3)), 2)
+
+
+def test_helpers_default_grid():
+    from pyflation_b200 import helpers
+    kend = helpers.getkend(0.85e-60, 0.4e-60, 1025)
+    assert kend == pytest.approx(8.2165e-58, rel=1e-12)
+    k = helpers.seq(0.85e-60, kend, 0.4e-60)
+    assert len(k) == 2053 and k[0] == 0.85e-60                 # BASELINE config 1 grid
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, not compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from pyflation_b200 import cosmomodels as c, rk4, _lib
+    m = c.FOCanonicalTwoStage(k=np.array([1e-60]), potential_func="msqphisq")
+    with pytest.raises(_lib.LibraryError):
+        m.run(saveresults=False)
+    with pytest.raises(NotImplementedError):
+        rk4.rkdriver_tsix(np.ones(2), 0.0, np.array([0]), 1.0, 0.01, lambda y, t: -y)
+    with pytest.raises(NotImplementedError):
+        c.CanonicalFirstOrder(k=np.array([1.0]), ystart=np.ones(5)).derivs(np.ones((5, 1)), 0.0)
+    with pytest.raises(rk4.SimRunError):
+        rk4.rkdriver_tsix(np.ones((3, 1)), 0.0, np.array([0]), 1.0, None,
+                          c.CanonicalBackground(ystart=np.array([18.0, -0.1, 1e-5])).derivs)
+    with pytest.raises(rk4.SimRunError):
+        rk4.rkdriver_tsix(np.ones((3, 1)), 0.0, np.array([500]), 1.0, 0.01,
+                          c.CanonicalBackground(ystart=np.array([18.0, -0.1, 1e-5])).derivs)
