@@ -1,0 +1,407 @@
+"""bench.py -- headline benchmark of the first-order RK4 hot path (contract: see DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): single-field lambdaphi4, 2^16 k-modes per GPU on
+linspace(0.85e-60, 8.2165e-58, N*2^16), cq=50, h=0.01, full trajectory output (41 GB per GPU).
+A "step" is one complete first-order integration of the rank's k-slab: background RK4 (K1),
+stage table (K1b) and the mode kernel (K2) writing yresult[T][5][nk] into HBM.
+
+  value  : k-mode*RK4-steps/s = sum_k (T-1-tsix_k) * K / (max over ranks of the device time of K
+           steps), inputs resident in HBM, output left in HBM.
+  e2e    : the same metric through the public API rk4.rkdriver_tsix(...) with host buffers:
+           every step copies the start vectors host->device and delivers the full yresult into
+           (pinned) host memory, device->host copies inside the timed region.
+  roofline : the mode kernel K2 against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+  cpu_baseline / --impl reference : the NumPy oracle port of the reference's rkdriver_tsix +
+           CanonicalFirstOrder.derivs on the host cores, one process per core, each on a
+           contiguous k-shard of a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+KMIN, KMAX = 0.85e-60, 8.2165e-58
+NK_PER_GPU = 2 ** 16
+POTENTIAL, NFIELDS, BGYSTART = "lambdaphi4", 1, [25.0, 0.0, 0.0]
+POT_PARAMS = {"nfields": 1}
+H, TEND, CQ = 0.01, 83.0, 50
+METRIC = "k-mode·RK4-steps/s (fp64)"
+UNIT = "k-mode·RK4-steps/s"
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference, all host cores
+# ------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """Integrate one contiguous k-shard with the NumPy oracle (rk4.py:58-138 restated)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import warnings
+    warnings.filterwarnings("ignore")
+    import pyflation_oracle as O
+    k, tsix, y0, ainit, fotend = args
+    t0 = time.perf_counter()
+    _, y = O.rk4_drive(y0, 0.0, tsix, fotend, H, O.make_fo_rhs(POTENTIAL, POT_PARAMS, NFIELDS, k, ainit))
+    dt = time.perf_counter() - t0
+    T = y.shape[0]
+    ok = bool(np.isfinite(y[-1, 3:, :]).all())
+    return dt, float(np.sum(T - 1 - tsix)), ok
+
+
+class CpuArm(object):
+    """Bounded sample of the bench workload for the host cores: P shards of `nk_worker`
+    consecutive modes of the 2^16 grid (each shard's column 0 is its own smallest k)."""
+
+    def __init__(self, nk_worker, cores=None):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import warnings
+        warnings.filterwarnings("ignore")
+        import pyflation_oracle as O
+        self.cores = cores or os.cpu_count() or 1
+        self.nk_worker = int(nk_worker)
+        nk = self.cores * self.nk_worker
+        kfull = np.linspace(KMIN, KMAX, NK_PER_GPU)
+        # spread the shards over the grid so the sample sees the whole range of start rows
+        starts = np.linspace(0, NK_PER_GPU - self.nk_worker, self.cores).astype(int)
+        k = np.concatenate([kfull[s:s + self.nk_worker] for s in starts])
+        ic = O.first_order_run(POTENTIAL, k, NFIELDS, POT_PARAMS, np.array(BGYSTART), cq=CQ,
+                               tend=TEND, h=H, integrate=False)
+        self.jobs = []
+        for w in range(self.cores):
+            sl = slice(w * self.nk_worker, (w + 1) * self.nk_worker)
+            self.jobs.append((k[sl], ic["fotstartindex"][sl], ic["foystart"][:, sl].copy(),
+                              ic["ainit"], ic["fotend"]))
+        self.sample = ("%d processes x %d consecutive modes of the %s 2^16 grid (%d modes), full "
+                       "T=%d trajectory each, NumPy oracle port of rkdriver_tsix"
+                       % (self.cores, self.nk_worker, POTENTIAL, nk,
+                          O.number_of_steps(0.0, ic["fotend"], H)))
+        import multiprocessing as mp
+        self.pool = mp.get_context("fork").Pool(self.cores)
+
+    def step(self):
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_worker, self.jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+        assert all(r[2] for r in res), "oracle produced non-finite modes"
+        return wall, sum(r[1] for r in res)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total = max(1, args.steps + args.warmup)
+    nk_worker = int(min(2048, max(128, 2048 * 15 // total)))
+    arm = CpuArm(nk_worker)
+    for _ in range(args.warmup):
+        arm.step()
+    wall = 0.0
+    work = 0.0
+    for _ in range(args.steps):
+        w, s = arm.step()
+        wall += w
+        work += s
+    arm.close()
+    value = work / wall
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port",
+                         "sample": arm.sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(ngpu):
+    return {"workload": "lambdaphi4 first-order run, 2^16 k-modes per GPU, full trajectory "
+                        "output (BASELINE.json configs[1])",
+            "potential": POTENTIAL, "nfields": NFIELDS, "nk_per_gpu": NK_PER_GPU,
+            "nk_total": NK_PER_GPU * ngpu, "k_range": [KMIN, KMAX], "cq": CQ, "h": H,
+            "tend": TEND, "output": "full trajectory yresult[T][5][nk] complex128",
+            "sharding": "contiguous k-slab per GPU, no data-path collective",
+            "l2": "no flush needed: each step streams a 41 GB write-once output (>> 126 MB L2), "
+                  "nothing is re-read"}
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, device_index):
+        threading.Thread.__init__(self, daemon=True)
+        self.samples, self.reasons, self.stop_flag = [], set(), False
+        self.max_mhz = None
+        self.ok = False
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as err:             # NVML missing: report it, do not fail the bench
+            self.err = repr(err)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def result(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [],
+                    "note": "no NVML samples"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # CPU baseline first (N=1 only), before this process touches CUDA: the workers are forked
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        arm = CpuArm(nk_worker=1024)
+        arm.step() if args.cpu_warmup else None
+        wall, work = arm.step()
+        arm.close()
+        cpu_baseline = {"value": work / wall, "unit": UNIT, "cores": arm.cores, "kind": "port",
+                        "sample": arm.sample, "wall_s": wall}
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from pyflation_b200 import cosmomodels, engine, rk4
+
+    # ---- synthetic inputs: this rank's contiguous k-slab of the global grid
+    kglobal = np.linspace(KMIN, KMAX, NK_PER_GPU * world)
+    k = kglobal[rank * NK_PER_GPU:(rank + 1) * NK_PER_GPU].copy()
+    m = cosmomodels.FOCanonicalTwoStage(k=k, potential_func=POTENTIAL, pot_params=dict(POT_PARAMS),
+                                        nfields=NFIELDS, bgystart=np.array(BGYSTART), cq=CQ,
+                                        tend=TEND, tstep_wanted=H)
+    m.runbg()
+    m.setfoics()
+    T = int(np.around((m.fotend - 0.0) / H) + 1)
+    pm = engine.make_model(POTENTIAL, POT_PARAMS, NFIELDS, m.ainit)
+    prob = engine.FirstOrderProblem(pm, k, m.fotstartindex, m.foystart, 0.0, T, H)
+    n0 = int(m.fotstartindex.min())
+    y0 = np.real(m.foystart[0:3, 0]).copy()
+    nvar = prob.nvar
+    mode_steps = float(np.sum(T - 1 - m.fotstartindex))
+    out = torch.empty((T, nvar, NK_PER_GPU), dtype=torch.complex128, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(evs=None):
+        prob.build_tables(y0, n0)                       # K1 + K1b
+        if evs is not None:
+            evs[0].record()
+        prob.launch(0, T, out, 1)                       # K2
+        if evs is not None:
+            evs[1].record()
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    k2_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                 for _ in range(args.steps)]
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for i in range(args.steps):
+        one_step(k2_events[i])
+    stop.record()
+    barrier()
+    sampler.stop_flag = True
+    sampler.join()
+    prob.check_flags()
+    elapsed_ms = start.elapsed_time(stop)
+    k2_ms = float(np.mean([a.elapsed_time(b) for a, b in k2_events]))
+    t = torch.tensor([elapsed_ms, k2_ms], dtype=torch.float64, device="cuda")
+    work = torch.tensor([mode_steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    elapsed_ms, k2_ms = float(t[0]), float(t[1])
+    total_work = float(work[0])
+    value = total_work * args.steps / (elapsed_ms * 1e-3)
+
+    # sanity: the last timed step produced a finite spectrum (work was really done)
+    pr = engine.pr_spectrum_device(NFIELDS, out[T - 1:T], prob.k)
+    assert bool(torch.isfinite(pr).all()) and float(pr.min()) > 0
+
+    # ---- roofline of the dominant kernel (K2)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)" if "hbm_gbs" in peaks \
+        else "fallback 6650 GB/s (B200_PROFILING.md)"
+    alg_bytes = mode_steps * 16 * nvar                        # 16*nvar B per mode-step
+    all_rows_bytes = float(T) * nvar * NK_PER_GPU * 16        # incl. mandatory NaN / start rows
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "k2_ncu_summary.json")))
+        traffic = prof.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "fo_rk4_kernel<1,2> (K2)",
+                "achieved": alg_bytes / (k2_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": alg_bytes / (k2_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
+                "peak_source": peak_src, "kernel_ms": k2_ms,
+                "algorithmic_bytes": alg_bytes,
+                "achieved_all_rows": all_rows_bytes / (k2_ms * 1e-3) / 1e9,
+                "frac_all_rows": all_rows_bytes / (k2_ms * 1e-3) / 1e9 / peak,
+                "note": "achieved counts 80 B per ACTIVE mode-step (SURVEY 8d); the output "
+                        "contract also requires the NaN rows before each mode's start, which "
+                        "achieved_all_rows includes (bytes the kernel must write per launch)"}
+    del out
+    torch.cuda.empty_cache()
+
+    # ---- e2e through the public API with host buffers
+    e2e = None if args.no_e2e else run_e2e(args, m, T, nvar, mode_steps, world, rank, barrier)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(world),
+            "clocks": sampler.result(), "e2e": e2e, "gpu_launches": 3 * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "T": T, "mode_steps_per_gpu_step": mode_steps,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, m, T, nvar, mode_steps, world, rank, barrier):
+    """rk4.rkdriver_tsix through the model's run(): host start vectors in, host yresult out."""
+    import torch
+    import torch.distributed as dist
+    import psutil
+    from pyflation_b200 import cosmomodels, engine
+    need = T * nvar * NK_PER_GPU * 16
+    local = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    avail = psutil.virtual_memory().available / max(1, local)
+    full = need < 0.6 * avail
+    host_rows = T if full else max(1, int((2 << 30) // (nvar * NK_PER_GPU * 16)))
+    host = engine._pinned_empty((host_rows, nvar, NK_PER_GPU), torch.complex128)
+    from pyflation_b200 import rk4
+    ystart_host = torch.as_tensor(m.foystart).pin_memory().numpy()
+    tsix_host = torch.as_tensor(np.ascontiguousarray(m.fotstartindex)).pin_memory().numpy()
+    fo = cosmomodels.CanonicalFirstOrder(ystart=ystart_host, tstart=m.fotstart, simtstart=0.0,
+                                         tstartindex=tsix_host, tend=m.fotend, tstep_wanted=H,
+                                         k=m.k, ainit=m.ainit, potential_func=POTENTIAL,
+                                         pot_params=dict(POT_PARAMS), nfields=NFIELDS)
+
+    def step():
+        if full:
+            # the user-facing call: numpy start vectors in, numpy yresult (pinned buffer) out
+            rk4.rkdriver_tsix(ystart=ystart_host, simtstart=0.0, tsix=tsix_host, tend=m.fotend,
+                              h=H, derivs=fo.derivs, yresult_out=host)
+        else:
+            pm = engine.make_model(POTENTIAL, POT_PARAMS, NFIELDS, m.ainit)
+            prob = engine.FirstOrderProblem(pm, m.k, tsix_host, ystart_host, 0.0, T, H)
+            prob.build_tables(np.real(ystart_host[0:3, 0]), int(tsix_host.min()))
+            engine.first_order_host(prob, ring=host)
+            prob.check_flags()
+
+    nsteps = max(1, min(args.steps, args.e2e_steps))
+    step()                                               # warm-up (page faults of the pinned buffer)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(nsteps):
+        step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    ww = torch.tensor([mode_steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ww, op=dist.ReduceOp.SUM)
+    if full:
+        last = host[T - 1].numpy()
+        assert np.isfinite(last[3:]).all()
+    h2d = int(ystart_host.size * 16 + m.k.size * 8 + tsix_host.size * 8)
+    return {"value": float(ww[0]) * nsteps / float(tt[0]), "unit": UNIT,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(need), "steps": nsteps,
+            "ms_per_step": 1e3 * float(tt[0]) / nsteps,
+            "host_buffer": "full pinned yresult" if full else "pinned ring (host RAM too small for N full results)",
+            "api": "rk4.rkdriver_tsix(ystart, simtstart, tsix, tend, h, derivs=CanonicalFirstOrder.derivs, "
+                   "yresult_out=<pinned buffer>)" if full else "engine.first_order_host(ring=...)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3, dest="e2e_steps")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only")
+    ap.add_argument("--cpu-warmup", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

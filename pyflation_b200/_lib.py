@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpyflation_b200.so")
+# PYFLATION_B200_LIB selects an alternative build of the same ABI (kernel tuning experiments)
+LIB_PATH = os.environ.get("PYFLATION_B200_LIB", os.path.join(_HERE, "lib", "libpyflation_b200.so"))
 
 PF_MAX_NFIELDS = 8
 PF_MAX_PARAMS = 8

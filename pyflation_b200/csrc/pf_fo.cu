@@ -19,54 +19,9 @@
 // copies (cp.async.bulk + mbarrier complete_tx); every thread of the CTA reads the same record,
 // i.e. conflict-free broadcast loads.
 #include "pf_common.cuh"
+#include "pf_fo_shared.cuh"
 
 namespace pf {
-
-struct FoArgs {
-    int64_t nk;
-    const double* __restrict__ k;
-    const int64_t* __restrict__ tsix;
-    const double* __restrict__ ystart;   // c128 [nvar][nk]
-    const double* __restrict__ rec;      // [T][REC]
-    int64_t T, t0, t1;
-    double* __restrict__ state;          // c128 [2 nf^2][nk]
-    double* __restrict__ yout;           // c128 [rows][nvar][nk]
-    int64_t out_every;
-    int32_t* flags;
-    double h;
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
 
 template <int NF>
 struct FoShape {
@@ -76,16 +31,25 @@ struct FoShape {
     static constexpr int BG_OFF = 4 * SW;           // background row sits after the 4 stages
     static constexpr int CH_RAW = 16384 / (REC * 8);
     static constexpr int CH = CH_RAW > 64 ? 64 : (CH_RAW < 8 ? 8 : CH_RAW);  // steps per chunk
-    static constexpr int BLOCK = 128;
+#ifndef PF_FO_BLOCK
+#define PF_FO_BLOCK 128
+#endif
+    static constexpr int BLOCK = PF_FO_BLOCK;
 };
+
+template <class T>
+__device__ __forceinline__ void plain_store(T* p, T v) { *p = v; }
 
 // one complex (NC = 2) or one real component (NC = 1) per row, per thread
 template <int NC>
 __device__ __forceinline__ void store_row(double* rowbase, int64_t kk, int part, const double (&c)[NC]) {
+#ifndef PF_STORE
+#define PF_STORE __stcs
+#endif
     if constexpr (NC == 2) {
-        __stcs(reinterpret_cast<double2*>(rowbase) + kk, make_double2(c[0], c[1]));
+        PF_STORE(reinterpret_cast<double2*>(rowbase) + kk, make_double2(c[0], c[1]));
     } else {
-        __stcs(rowbase + 2 * kk + part, c[0]);
+        PF_STORE(rowbase + 2 * kk + part, c[0]);
     }
 }
 
@@ -344,8 +308,12 @@ extern "C" int pf_fo_run(const pf_model* m, int64_t nk, const double* k_dev, con
     a.yout = out_every > 0 ? yout_dev : nullptr; a.out_every = out_every; a.flags = flags_dev;
     a.h = h;
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool generic_only = getenv("PF_FO_GENERIC") != nullptr;
     switch (m->nfields) {
-        case 1: launch_fo<1, 2>(a, st); break;
+        case 1:
+            if (out_every == 1 && !generic_only) launch_fo1(a, st);   // full-trajectory fast path
+            else launch_fo<1, 2>(a, st);
+            break;
         case 2: launch_fo<2, 2>(a, st); break;
         case 3: launch_fo<3, 1>(a, st); break;
         case 4: launch_fo<4, 1>(a, st); break;

@@ -1,0 +1,56 @@
+// Argument block and TMA / mbarrier helpers shared by the first-order kernels.
+#pragma once
+#include "pf_common.cuh"
+
+namespace pf {
+
+struct FoArgs {
+    int64_t nk;
+    const double* __restrict__ k;
+    const int64_t* __restrict__ tsix;
+    const double* __restrict__ ystart;   // c128 [nvar][nk]
+    const double* __restrict__ rec;      // [T][REC]
+    int64_t T, t0, t1;
+    double* __restrict__ state;          // c128 [2 nf^2][nk]
+    double* __restrict__ yout;           // c128 [rows][nvar][nk]
+    int64_t out_every;
+    int32_t* flags;
+    double h;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+
+int launch_fo1(const FoArgs& a, cudaStream_t st);   // pf_fo1.cu
+
+}  // namespace pf

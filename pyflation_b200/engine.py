@@ -159,14 +159,22 @@ def plan_window(T, nvar, nk, slab_bytes):
     return rows
 
 
-def first_order_host(prob, out=None, slab_bytes=1 << 30):
+def first_order_host(prob, out=None, slab_bytes=1 << 30, ring=None):
     """Trajectory delivered into host memory: time windows ping-pong between two device slabs;
     the device->host copy of window w overlaps the integration of window w+1.
-    Returns a torch CPU tensor (T, nvar, nk) complex128 (pinned when it could be)."""
+    Returns a torch CPU tensor (T, nvar, nk) complex128 (pinned when it could be).
+
+    ``ring``: a (R, nvar, nk) host tensor used instead of a full-size result when host memory
+    cannot hold it -- every row still crosses to the host, windows overwrite each other."""
     T, nvar, nk = prob.T, prob.nvar, prob.nk
-    if out is None:
-        out = _pinned_empty((T, nvar, nk), torch.complex128)
     W = plan_window(T, nvar, nk, slab_bytes)
+    if ring is not None:
+        W = max(1, min(W, ring.shape[0] // 2))
+    elif out is None:
+        out = _pinned_empty((T, nvar, nk), torch.complex128)
+    elif tuple(out.shape) != (T, nvar, nk) or out.dtype != torch.complex128 or not out.is_contiguous():
+        raise ValueError("output buffer must be a contiguous complex128 tensor of shape %r"
+                         % ((T, nvar, nk),))
     with torch.cuda.device(prob.dev):
         slabs = [torch.empty((W, nvar, nk), dtype=torch.complex128, device=prob.dev)
                  for _ in range(2 if W < T else 1)]
@@ -184,14 +192,15 @@ def first_order_host(prob, out=None, slab_bytes=1 << 30):
             done.record(compute)
             copier.wait_event(done)
             with torch.cuda.stream(copier):
-                out[t0:t1].copy_(slabs[b][:t1 - t0], non_blocking=True)
+                dst = out[t0:t1] if ring is None else ring[(w % 2) * W:(w % 2) * W + (t1 - t0)]
+                dst.copy_(slabs[b][:t1 - t0], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copier)
             copied[b] = ev
             w += 1
         copier.synchronize()
         compute.synchronize()
-    return out
+    return out if ring is None else ring
 
 
 def pr_spectrum_device(nf, y, k=None):

@@ -30,6 +30,17 @@ def main(pot="lambdaphi4", nf=1, nk=2**16, bgy=(25.0, 0.0, 0.0), params=None):
         ms = e0.elapsed_time(e1)
         print("K2 %.3f ms  %.3e mode-steps/s  write %.1f GB/s (all rows) %.1f GB/s (active)" % (
             ms, steps / ms * 1e3, out.numel() * 16 / ms / 1e6, steps * 16 * prob.nvar / ms / 1e6))
+    if os.environ.get("PF_FILL_PROBE"):
+        flat = out.view(torch.float64).view(-1)
+        for rep in range(3):
+            e0, e1 = ev(), ev()
+            e0.record(); flat.fill_(1.5); e1.record(); torch.cuda.synchronize()
+            print("torch fill %.3f ms %.1f GB/s" % (e0.elapsed_time(e1), flat.numel() * 8 / e0.elapsed_time(e1) / 1e6))
+        half = flat.numel() // 2
+        for rep in range(3):
+            e0, e1 = ev(), ev()
+            e0.record(); flat[:half].copy_(flat[half:2 * half]); e1.record(); torch.cuda.synchronize()
+            print("torch copy %.3f ms %.1f GB/s (r+w)" % (e0.elapsed_time(e1), half * 16 / e0.elapsed_time(e1) / 1e6))
     prob.check_flags()
     print("T", T, "nk", nk, "tsix", m.fotstartindex.min(), m.fotstartindex.max())
 
