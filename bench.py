@@ -242,10 +242,9 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
 
     def one_step(evs=None):
-        prob.build_tables(y0, n0)                       # K1 + K1b
         if evs is not None:
             evs[0].record()
-        prob.launch(0, T, out, 1)                       # K2
+        prob.solve(y0, n0, T, out, 1)                   # ONE fused launch: K1 + K1b + K2
         if evs is not None:
             evs[1].record()
 
@@ -298,7 +297,7 @@ def run_gpu_arm(args):
         traffic = prof.get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "fo_rk4_kernel<1,2> (K2)",
+    roofline = {"bound": "hbm", "kernel": "fo1_fused_kernel<lambdaphi4> (K1+K1b+K2 in one launch)",
                 "achieved": alg_bytes / (k2_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": alg_bytes / (k2_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
                 "peak_source": peak_src, "kernel_ms": k2_ms,
@@ -320,7 +319,7 @@ def run_gpu_arm(args):
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(world),
-            "clocks": sampler.result(), "e2e": e2e, "gpu_launches": 3 * args.steps,
+            "clocks": sampler.result(), "e2e": e2e, "gpu_launches": args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "T": T, "mode_steps_per_gpu_step": mode_steps,
         }
@@ -357,8 +356,8 @@ def run_e2e(args, m, T, nvar, mode_steps, world, rank, barrier):
         else:
             pm = engine.make_model(POTENTIAL, POT_PARAMS, NFIELDS, m.ainit)
             prob = engine.FirstOrderProblem(pm, m.k, tsix_host, ystart_host, 0.0, T, H)
-            prob.build_tables(np.real(ystart_host[0:3, 0]), int(tsix_host.min()))
-            engine.first_order_host(prob, ring=host)
+            engine.first_order_host(prob, ring=host, y0=np.real(ystart_host[0:3, 0]),
+                                    n0=int(tsix_host.min()))
             prob.check_flags()
 
     nsteps = max(1, min(args.steps, args.e2e_steps))

@@ -135,6 +135,23 @@ int pf_fo_run(const pf_model *m, int64_t nk, const double *k_dev, const int64_t 
               int64_t t0, int64_t t1, double *state_dev, double *yout_dev, int64_t out_every,
               int32_t *flags_dev, void *stream);
 
+/* ---- one-call solve of the first window [0, t1): K1 + K1b + K2 ----
+ * What rk4.rkdriver_tsix does for a CanonicalFirstOrder model in one call.  For single-field
+ * runs with full-trajectory output (out_every == 1) this is ONE fused launch: a producer CTA
+ * integrates the background and publishes the step records while the other CTAs integrate the
+ * modes (they acquire the published count before each record chunk), so K1 hides behind K2.
+ * Otherwise it issues pf_bg_run, pf_stage_table, pf_fo_run back to back.
+ *   n0, y0_host  : column 0's start row and its background values (real parts of ystart[0:2nf+1, 0])
+ *   scratch_dev  : pf_solve_scratch_doubles(nf, T) doubles; on return its first
+ *                  T*pf_rec_doubles(nf) doubles are the records, valid as rec_dev for
+ *                  pf_fo_run on later windows [t0 > 0, t1')
+ *   ws_dev       : int32[8], zeroed by the call; ws_dev[1] holds the PF_FLAG_* bits afterwards */
+int64_t pf_solve_scratch_doubles(int nfields, int64_t T);
+int pf_fo_solve(const pf_model *m, int64_t nk, const double *k_dev, const int64_t *tsix_dev,
+                const double *ystart_dev, int64_t n0, const double *y0_host, int64_t T,
+                double simtstart, double h, int64_t t1, double *scratch_dev, double *state_dev,
+                double *yout_dev, int64_t out_every, int32_t *ws_dev, void *stream);
+
 /* ---- K5: curvature power spectrum of trajectory rows (adiabatic.py:153-285) ----
  * y_dev c128 [nrows][nvar][nk] -> Pr_dev [nrows][nk];  if k_dev != NULL the result is the
  * scaled spectrum k^3/(2 pi^2) P_R (utilities.py:12-37). */

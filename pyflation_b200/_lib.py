@@ -19,8 +19,8 @@ EXPORTS = [
     "pf_version", "pf_last_error", "pf_potential_id", "pf_potential_name",
     "pf_potential_nfields", "pf_potential_nparams", "pf_potential_param_name",
     "pf_potential_param_default", "pf_potential_eval", "pf_number_of_steps", "pf_nvar",
-    "pf_rec_doubles", "pf_bg_run", "pf_stage_table", "pf_fo_run", "pf_pr_spectrum",
-    "pf_scatter_slab",
+    "pf_rec_doubles", "pf_bg_run", "pf_stage_table", "pf_fo_run", "pf_solve_scratch_doubles",
+    "pf_fo_solve", "pf_pr_spectrum", "pf_scatter_slab",
 ]
 
 
@@ -81,6 +81,10 @@ def lib():
     L.pf_stage_table.argtypes = [mp, c_i64, c_dbl, c_dbl, c_i64, c_vp, c_vp, c_vp, c_vp]
     L.pf_fo_run.argtypes = [mp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_dbl, c_i64, c_i64,
                             c_vp, c_vp, c_i64, c_vp, c_vp]
+    L.pf_solve_scratch_doubles.argtypes = [c_int, c_i64]
+    L.pf_solve_scratch_doubles.restype = c_i64
+    L.pf_fo_solve.argtypes = [mp, c_i64, c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(c_dbl), c_i64, c_dbl,
+                              c_dbl, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]
     L.pf_pr_spectrum.argtypes = [c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]
     L.pf_scatter_slab.argtypes = [c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]
     _lib = L

@@ -6,11 +6,11 @@
 // the stage coefficients are the k-independent factors of CanonicalFirstOrder.derivs
 // (cosmomodels.py:637-674) evaluated at the RK4 stage arguments of the background.
 #include "pf_common.cuh"
+#include "pf_fo_shared.cuh"
 #include "pf_potentials.cuh"
 
 namespace pf {
 
-struct PotParams { double v[PF_MAX_PARAMS]; };
 struct BgState { double v[2 * PF_MAX_NFIELDS + 1]; };
 
 template <int POT, int NF>

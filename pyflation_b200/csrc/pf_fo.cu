@@ -326,3 +326,46 @@ extern "C" int pf_fo_run(const pf_model* m, int64_t nk, const double* k_dev, con
     PF_CUDA_CHECK(cudaGetLastError(), "pf_fo_run launch");
     return PF_OK;
 }
+
+extern "C" int64_t pf_solve_scratch_doubles(int nfields, int64_t T) {
+    if (nfields < 1 || nfields > PF_MAX_NFIELDS || T < 0) return -1;
+    return T * (int64_t)(rec_of(nfields) + 5 * nbg_of(nfields));
+}
+
+extern "C" int pf_fo_solve(const pf_model* m, int64_t nk, const double* k_dev, const int64_t* tsix_dev,
+                           const double* ystart_dev, int64_t n0, const double* y0_host, int64_t T,
+                           double simtstart, double h, int64_t t1, double* scratch_dev,
+                           double* state_dev, double* yout_dev, int64_t out_every, int32_t* ws_dev,
+                           void* stream) {
+    int rc = check_model(m);
+    if (rc) return rc;
+    if (nk < 0 || T < 1 || t1 < 0 || t1 > T || out_every < 0) { set_error("pf_fo_solve: bad sizes"); return PF_E_ARG; }
+    if (!(h == h) || h == 0.0) { set_error("pf_fo_solve: Need to specify h."); return PF_E_STEP; }
+    if (n0 < 0 || n0 >= T) { set_error("pf_fo_solve: Start times outside range of steps."); return PF_E_START; }
+    if (!y0_host || !scratch_dev || !ws_dev) { set_error("pf_fo_solve: null buffer"); return PF_E_ARG; }
+    if (nk > 0 && (!k_dev || !tsix_dev || !ystart_dev)) { set_error("pf_fo_solve: null buffer"); return PF_E_ARG; }
+    if (out_every > 0 && !yout_dev) { set_error("pf_fo_solve: out_every > 0 needs yout_dev"); return PF_E_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nf = m->nfields;
+    double* rec = scratch_dev;
+    double* stagey = rec + T * (int64_t)rec_of(nf);
+    double* bg = stagey + T * (int64_t)(4 * nbg_of(nf));
+    PF_CUDA_CHECK(cudaMemsetAsync(ws_dev, 0, 8 * sizeof(int32_t), st), "pf_fo_solve memset");
+    static const bool no_fuse = getenv("PF_FO_NOFUSE") != nullptr;
+    if (nf == 1 && out_every == 1 && nk > 0 && t1 > 0 && !no_fuse) {
+        FoArgs a;
+        a.nk = nk; a.k = k_dev; a.tsix = tsix_dev; a.ystart = ystart_dev; a.rec = rec;
+        a.T = T; a.t0 = 0; a.t1 = t1; a.state = state_dev; a.yout = yout_dev; a.out_every = 1;
+        a.flags = ws_dev + 1; a.h = h;
+        if (launch_fo1_fused(m, a, simtstart, n0, y0_host, rec, ws_dev, st)) {
+            PF_CUDA_CHECK(cudaGetLastError(), "pf_fo_solve fused launch");
+            return PF_OK;
+        }
+    }
+    rc = pf_bg_run(m, T, h, n0, y0_host, bg, stagey, stream);
+    if (rc) return rc;
+    rc = pf_stage_table(m, T, simtstart, h, n0, bg, stagey, rec, stream);
+    if (rc) return rc;
+    return pf_fo_run(m, nk, k_dev, tsix_dev, ystart_dev, rec, T, h, 0, t1, state_dev, yout_dev, out_every,
+                     ws_dev + 1, stream);
+}

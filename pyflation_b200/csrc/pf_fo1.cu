@@ -13,6 +13,7 @@
 //     of CTAs per SM (148 SMs) -- see pf_fo_run.
 #include "pf_common.cuh"
 #include "pf_fo_shared.cuh"
+#include "pf_potentials.cuh"
 
 namespace pf {
 
@@ -66,15 +67,33 @@ __device__ __forceinline__ void rk4_mode(const Coef& c, double kval, double h, d
     }
 }
 
+// Fused launches: records are produced by another CTA of the same grid; wait (acquire) until
+// `need` of them are published, then order the generic-proxy writes before the TMA read.
+__device__ __forceinline__ void wait_progress(const long long* progress, long long need) {
+    long long have;
+    unsigned spins = 0;
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.s64 %0, [%1];" : "=l"(have) : "l"(progress) : "memory");
+        if (have >= need) break;
+        __nanosleep(128);
+        if (++spins > (1u << 27)) __trap();           // ~20 s: the producer died; fail, do not hang
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+// Consumer: integrates the modes of logical CTA `cta` (nthreads threads, KPT modes each).
+// `progress` (may be null) is the producer's published record count in fused launches.
 template <int KPT>
-__global__ void __launch_bounds__(512) fo1_kernel(FoArgs a) {
+__device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nthreads,
+                                            const long long* progress) {
     __shared__ __align__(128) double srec[2][FO1_CH * FO1_REC];
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ long long s_tsmin, s_tsmax;
 
     const int tid = threadIdx.x;
+    if (tid >= nthreads) return;                      // fused launches may carry spare threads
     const int64_t nk = a.nk;
-    const int64_t kk0 = ((int64_t)blockIdx.x * blockDim.x + tid) * KPT;
+    const int64_t kk0 = (cta * nthreads + tid) * KPT;
 
     if (tid == 0) {
         s_tsmin = INT64_MAX;
@@ -135,6 +154,7 @@ __global__ void __launch_bounds__(512) fo1_kernel(FoArgs a) {
         const int64_t base = c0 + c * FO1_CH;
         const int64_t cnt = (a.t1 - base) < FO1_CH ? (a.t1 - base) : FO1_CH;
         const uint32_t bytes = (uint32_t)(cnt * FO1_REC * sizeof(double));
+        if (progress) wait_progress(progress, base + cnt);
         mbar_expect_tx(&bars[buf], bytes);
         bulk_g2s(&srec[buf][0], a.rec + base * FO1_REC, bytes, &bars[buf]);
     };
@@ -216,9 +236,142 @@ __global__ void __launch_bounds__(512) fo1_kernel(FoArgs a) {
     }
 }
 
+template <int KPT>
+__global__ void __launch_bounds__(512) fo1_kernel(FoArgs a) {
+    fo1_consume<KPT>(a, blockIdx.x, blockDim.x, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------
+// Producer CTA of the fused launch: K1 (serial background RK4) and K1b (step records) run
+// inside the same grid as the mode kernel, so their ~1.7 ms hide behind the trajectory stores.
+//   warp 0, lane 0 : the serial RK4 chain; writes the 4 stage arguments of every step into a
+//                    shared-memory ring and bumps s_head every 8 steps;
+//   warps 1-4      : 128 workers, one (step, stage) item each per 32-step batch: evaluate
+//                    A, R, C (potential 2nd derivative, exp) and write the record to global
+//                    memory; after a batch: __threadfence, named barrier, release-store of the
+//                    published record count that the consumer CTAs acquire.
+// ------------------------------------------------------------------------------------------
+constexpr int PROD_RING = 128;                        // steps of stage arguments in flight
+constexpr int PROD_THREADS = 160;
+
+struct ProdArgs {
+    PotParams par;
+    double ainit, simtstart;
+    double y0[3];
+    int64_t n0;
+    double* rec;                                      // [T][16]
+    int32_t* ws;                                      // [0] ticket, [1] flags, [2..3] progress (s64)
+};
+
+template <int POT>
+__device__ __forceinline__ void bg1_rhs(const double* __restrict__ p, double phi, double pd, double H,
+                                        double& dphi, double& dpd, double& dH) {
+    double f[1] = {phi}, dU[1], d2U[1], U;
+    potential<POT, 1, false>(p, f, U, dU, d2U);
+    const double invH2 = 1.0 / (H * H);
+    dphi = pd;                                        // cosmomodels.py:563
+    dpd = -(U * pd + dU[0]) * invH2;                  // :566
+    dH = -0.5 * (pd * pd) * H;                        // :569
+}
+
+template <int POT>
+__device__ __forceinline__ void fo1_produce(const FoArgs& a, const ProdArgs& f) {
+    __shared__ double ring[PROD_RING][12];
+    __shared__ volatile long long s_head, s_tail;
+    const int tid = threadIdx.x;
+    if (tid >= PROD_THREADS) return;
+    const int64_t T = a.T, n0 = f.n0;
+    long long* progress = reinterpret_cast<long long*>(f.ws + 2);
+    if (tid == 0) { s_head = n0; s_tail = n0; }
+    asm volatile("bar.sync 2, %0;" ::"n"(PROD_THREADS) : "memory");
+
+    if (tid < 32) {
+        if (tid != 0) return;
+        const double h = a.h, hh = h * 0.5, h6 = h / 6.0;
+        double y0 = f.y0[0], y1 = f.y0[1], y2 = f.y0[2];
+        for (int64_t n = n0; n < T; ++n) {
+            if ((n & 7) == 0) {
+                unsigned spins = 0;
+                while (n - s_tail > PROD_RING - 16) {
+                    if (++spins > (1u << 30)) __trap();
+                }
+            }
+            double* slot = ring[n % PROD_RING];
+            double a0, a1, a2, b0, b1, b2, c0, c1, c2, d0, d1, d2;
+            slot[0] = y0; slot[1] = y1; slot[2] = y2;
+            bg1_rhs<POT>(f.par.v, y0, y1, y2, a0, a1, a2);
+            double t0 = y0 + hh * a0, t1 = y1 + hh * a1, t2 = y2 + hh * a2;
+            slot[3] = t0; slot[4] = t1; slot[5] = t2;
+            bg1_rhs<POT>(f.par.v, t0, t1, t2, b0, b1, b2);
+            t0 = y0 + hh * b0; t1 = y1 + hh * b1; t2 = y2 + hh * b2;
+            slot[6] = t0; slot[7] = t1; slot[8] = t2;
+            bg1_rhs<POT>(f.par.v, t0, t1, t2, c0, c1, c2);
+            t0 = y0 + h * c0; t1 = y1 + h * c1; t2 = y2 + h * c2;
+            slot[9] = t0; slot[10] = t1; slot[11] = t2;
+            bg1_rhs<POT>(f.par.v, t0, t1, t2, d0, d1, d2);
+            y0 = y0 + h6 * (a0 + d0 + 2.0 * (c0 + b0));      // rk4.py:46,53
+            y1 = y1 + h6 * (a1 + d1 + 2.0 * (c1 + b1));
+            y2 = y2 + h6 * (a2 + d2 + 2.0 * (c2 + b2));
+            if ((n & 7) == 7 || n == T - 1) {
+                __threadfence_block();
+                s_head = n + 1;
+            }
+        }
+        return;
+    }
+
+    const int w = tid - 32;                           // 0..127
+    const int dn = w >> 2, s = w & 3;
+    for (int64_t b = n0; b < T; b += 32) {
+        const int64_t need = (b + 32 < T) ? b + 32 : T;
+        {
+            unsigned spins = 0;
+            while (s_head < need) {
+                if (++spins > (1u << 30)) __trap();
+            }
+            __threadfence_block();                    // ring reads stay behind the s_head read
+        }
+        const int64_t n = b + dn;
+        if (n < T) {
+            const double* slot = ring[n % PROD_RING] + 3 * s;
+            const double phi = slot[0], pd = slot[1], H = slot[2];
+            const double x = f.simtstart + (double)n * a.h;           // rk4.py:118 last_x
+            const double t = (s == 0) ? x : ((s == 3) ? x + a.h : x + a.h * 0.5);
+            const double sf = f.ainit * exp(t);                       // cosmomodels.py:637
+            double ff[1] = {phi}, dU[1], d2U[1], U;
+            potential<POT, 1, true>(f.par.v, ff, U, dU, d2U);
+            const double invH2 = 1.0 / (H * H);
+            double* r = f.rec + n * FO1_REC;
+            r[3 * s + 0] = U * invH2;
+            r[3 * s + 1] = 1.0 / (sf * H);
+            r[3 * s + 2] = (d2U[0] + pd * dU[0] + dU[0] * pd + pd * pd * U) * invH2;   // :667-674
+            if (s == 0) { r[12] = phi; r[13] = pd; r[14] = H; r[15] = 0.0; }
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (w == 0) {
+            s_tail = need;
+            asm volatile("st.release.gpu.global.s64 [%0], %1;" ::"l"(progress), "l"((long long)need) : "memory");
+        }
+    }
+}
+
+template <int POT>
+__global__ void __launch_bounds__(512) fo1_fused_kernel(FoArgs a, ProdArgs f, int cthreads) {
+    __shared__ int s_cta;
+    if (threadIdx.x == 0) s_cta = atomicAdd(f.ws, 1);   // ticket: the first CTA to run produces
+    __syncthreads();
+    const int cta = s_cta;
+    if (cta == 0) {
+        fo1_produce<POT>(a, f);
+        return;
+    }
+    fo1_consume<1>(a, cta - 1, cthreads, reinterpret_cast<const long long*>(f.ws + 2));
+}
+
 // Grid shape: a whole number c of CTAs per SM, c the smallest for which a CTA holds at most
 // `max_threads` threads (so every SM gets the same number of equally sized CTAs).
-int launch_fo1(const FoArgs& a, cudaStream_t st) {
+static int sm_count() {
     static int sms = 0;
     if (!sms) {
         int dev = 0;
@@ -226,24 +379,63 @@ int launch_fo1(const FoArgs& a, cudaStream_t st) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
     }
-    int kpt = 1, max_threads = 512;
-    if (const char* e = getenv("PF_FO1_KPT")) kpt = atoi(e);
+    return sms;
+}
+
+static int64_t fo1_block(int64_t nk, int sms) {
+    int max_threads = 512;
     if (const char* e = getenv("PF_FO1_MAXT")) max_threads = atoi(e);
-    if (kpt != 2) kpt = 1;
     if (max_threads < 32 || max_threads > 512) max_threads = 512;
-    int64_t threads_needed = (a.nk + kpt - 1) / kpt;
-    int64_t per_sm = 1;
     int64_t block = 0;
-    for (;; ++per_sm) {
-        block = (threads_needed + sms * per_sm - 1) / (sms * per_sm);
+    for (int64_t per_sm = 1;; ++per_sm) {
+        block = (nk + sms * per_sm - 1) / (sms * per_sm);
         block = (block + 31) / 32 * 32;
         if (block <= max_threads) break;
     }
     if (const char* e = getenv("PF_FO1_BLOCK")) block = atoi(e);
-    const int64_t grid = (threads_needed + block - 1) / block;
-    if (kpt == 2) fo1_kernel<2><<<(unsigned)grid, (unsigned)block, 0, st>>>(a);
-    else fo1_kernel<1><<<(unsigned)grid, (unsigned)block, 0, st>>>(a);
+    return block;
+}
+
+int launch_fo1(const FoArgs& a, cudaStream_t st) {
+    const int64_t block = fo1_block(a.nk, sm_count());
+    const int64_t grid = (a.nk + block - 1) / block;
+    fo1_kernel<1><<<(unsigned)grid, (unsigned)block, 0, st>>>(a);
     return 0;
+}
+
+// Fused K1 + K1b + K2 for nf = 1 (single-field potentials and nflation with one field).
+// Returns false when (potential, nfields) has no fused instantiation.
+bool launch_fo1_fused(const pf_model* m, const FoArgs& a, double simtstart, int64_t n0,
+                      const double* y0_host, double* rec, int32_t* ws, cudaStream_t st) {
+    ProdArgs f;
+    for (int i = 0; i < PF_MAX_PARAMS; ++i) f.par.v[i] = m->params[i];
+    f.ainit = m->ainit;
+    f.simtstart = simtstart;
+    f.y0[0] = y0_host[0]; f.y0[1] = y0_host[1]; f.y0[2] = y0_host[2];
+    f.n0 = n0;
+    f.rec = rec;
+    f.ws = ws;
+    const int64_t cthreads = fo1_block(a.nk, sm_count() - 1);   // one SM hosts the producer
+    const int64_t block = cthreads > PROD_THREADS ? cthreads : PROD_THREADS;
+    const int64_t grid = (a.nk + cthreads - 1) / cthreads + 1;
+#define PF_CALL(POT, NF) \
+    fo1_fused_kernel<POT><<<(unsigned)grid, (unsigned)block, 0, st>>>(a, f, (int)cthreads)
+    switch (m->potential_id) {
+        case PF_MSQPHISQ: PF_CALL(PF_MSQPHISQ, 1); break;
+        case PF_LAMBDAPHI4: PF_CALL(PF_LAMBDAPHI4, 1); break;
+        case PF_LINDE: PF_CALL(PF_LINDE, 1); break;
+        case PF_HYBRID2AND4: PF_CALL(PF_HYBRID2AND4, 1); break;
+        case PF_PHI2OVER3: PF_CALL(PF_PHI2OVER3, 1); break;
+        case PF_MSQPHISQ_WITHV0: PF_CALL(PF_MSQPHISQ_WITHV0, 1); break;
+        case PF_STEP_POTENTIAL: PF_CALL(PF_STEP_POTENTIAL, 1); break;
+        case PF_BUMP_POTENTIAL: PF_CALL(PF_BUMP_POTENTIAL, 1); break;
+        case PF_RESONANCE: PF_CALL(PF_RESONANCE, 1); break;
+        case PF_BUMP_NOTHIRDDERIV: PF_CALL(PF_BUMP_NOTHIRDDERIV, 1); break;
+        case PF_NFLATION: PF_CALL(PF_NFLATION, 1); break;
+        default: return false;
+    }
+#undef PF_CALL
+    return true;
 }
 
 }  // namespace pf

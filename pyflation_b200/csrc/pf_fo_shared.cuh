@@ -51,6 +51,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 
+struct PotParams { double v[PF_MAX_PARAMS]; };
+
 int launch_fo1(const FoArgs& a, cudaStream_t st);   // pf_fo1.cu
+bool launch_fo1_fused(const pf_model* m, const FoArgs& a, double simtstart, int64_t n0,
+                      const double* y0_host, double* rec, int32_t* ws, cudaStream_t st);
 
 }  // namespace pf

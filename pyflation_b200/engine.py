@@ -109,7 +109,9 @@ class FirstOrderProblem(object):
         self.ystart = as_dev(ystart, torch.complex128)
         if tuple(self.ystart.shape) != (self.nvar, self.nk):
             raise ValueError("ystart must have shape (%d, %d)" % (self.nvar, self.nk))
-        self.flags = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.ws = torch.zeros(8, dtype=torch.int32, device=self.dev)    # [1] = PF_FLAG_* bits
+        self.flags = self.ws[1:2]
+        self.scratch = None
         self.state = torch.zeros((2 * self.nf * self.nf, self.nk), dtype=torch.complex128,
                                  device=self.dev)
         self.rec = None
@@ -118,6 +120,28 @@ class FirstOrderProblem(object):
     def build_tables(self, y0, n0):
         self.bg, self.rec = background_tables(self.model, y0, self.T, self.h, self.simtstart,
                                               n0, True, self.dev)
+
+    def solve(self, y0, n0, t1, yout, out_every=1, stream=None):
+        """pf_fo_solve: K1 + K1b + K2 for the window [0, t1) -- one fused launch for single-field
+        full-trajectory runs.  Leaves the step records in ``self.rec`` for later windows."""
+        L = _lib.lib()
+        nf = self.nf
+        y0 = np.ascontiguousarray(np.asarray(y0, dtype=np.float64).reshape(-1))
+        if y0.shape[0] != 2 * nf + 1:
+            raise ValueError("background start vector must have %d entries" % (2 * nf + 1))
+        with torch.cuda.device(self.dev):
+            if self.scratch is None:
+                self.scratch = torch.empty(int(L.pf_solve_scratch_doubles(nf, self.T)),
+                                           dtype=torch.float64, device=self.dev)
+            _lib.check(L.pf_fo_solve(ctypes.byref(self.model), self.nk, _ptr(self.k), _ptr(self.tsix),
+                                     _ptr(self.ystart), int(n0),
+                                     y0.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), self.T,
+                                     self.simtstart, self.h, int(t1), _ptr(self.scratch),
+                                     _ptr(self.state), _ptr(yout),
+                                     int(out_every if yout is not None else 0), _ptr(self.ws),
+                                     _stream_ptr(stream)))
+        nrec = int(L.pf_rec_doubles(nf))
+        self.rec = self.scratch[:self.T * nrec].view(self.T, nrec)
 
     def launch(self, t0, t1, yout, out_every=1, stream=None):
         """K2: rows [t0, t1) -> yout (device c128 tensor or None)."""
@@ -136,14 +160,19 @@ class FirstOrderProblem(object):
                 "(DESIGN.md) and there is no per-column fallback")
 
 
-def first_order_device(prob, out=None, out_every=1):
+def first_order_device(prob, out=None, out_every=1, y0=None, n0=None):
     """Trajectory kept in HBM: returns a device tensor (ceil(T/out_every), nvar, nk) complex128
-    holding rows 0, out_every, 2*out_every, ... (out_every=1: the full trajectory)."""
+    holding rows 0, out_every, 2*out_every, ... (out_every=1: the full trajectory).
+    With ``y0, n0`` (column 0's background start) the tables are built by the same call
+    (pf_fo_solve); otherwise ``prob.build_tables`` must have run."""
     with torch.cuda.device(prob.dev):
         nrows = (prob.T + out_every - 1) // out_every
         if out is None:
             out = torch.empty((nrows, prob.nvar, prob.nk), dtype=torch.complex128, device=prob.dev)
-        prob.launch(0, prob.T, out, out_every)
+        if y0 is not None:
+            prob.solve(y0, n0, prob.T, out, out_every)
+        else:
+            prob.launch(0, prob.T, out, out_every)
     return out
 
 
@@ -159,7 +188,7 @@ def plan_window(T, nvar, nk, slab_bytes):
     return rows
 
 
-def first_order_host(prob, out=None, slab_bytes=1 << 30, ring=None):
+def first_order_host(prob, out=None, slab_bytes=1 << 30, ring=None, y0=None, n0=None):
     """Trajectory delivered into host memory: time windows ping-pong between two device slabs;
     the device->host copy of window w overlaps the integration of window w+1.
     Returns a torch CPU tensor (T, nvar, nk) complex128 (pinned when it could be).
@@ -187,7 +216,10 @@ def first_order_host(prob, out=None, slab_bytes=1 << 30, ring=None):
             b = w % len(slabs)
             if copied[b] is not None:
                 compute.wait_event(copied[b])           # slab b is free again
-            prob.launch(t0, t1, slabs[b], 1, compute)
+            if t0 == 0 and y0 is not None:
+                prob.solve(y0, n0, t1, slabs[b], 1, compute)     # K1 + K1b ride along
+            else:
+                prob.launch(t0, t1, slabs[b], 1, compute)
             done = torch.cuda.Event()
             done.record(compute)
             copier.wait_event(done)

@@ -119,11 +119,10 @@ def _run_first_order(model, ystart, simtstart, tsix, T, h, yresult_out=None):
     pm = engine.make_model(model.potential_func, model.pot_params, nf, model.ainit)
     prob = engine.FirstOrderProblem(pm, k, tsix, ystart.astype(np.complex128, copy=False),
                                     simtstart, T, h)
-    prob.build_tables(np.real(ystart[0:2 * nf + 1, 0]), n0)
     out = None
     if yresult_out is not None:
         out = yresult_out if torch.is_tensor(yresult_out) else torch.as_tensor(yresult_out)
-    res = engine.first_order_host(prob, out=out)
+    res = engine.first_order_host(prob, out=out, y0=np.real(ystart[0:2 * nf + 1, 0]), n0=n0)
     prob.check_flags()
     return yresult_out if (yresult_out is not None and not torch.is_tensor(yresult_out)) else res.numpy()
 

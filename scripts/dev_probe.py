@@ -41,6 +41,11 @@ def main(pot="lambdaphi4", nf=1, nk=2**16, bgy=(25.0, 0.0, 0.0), params=None):
             e0, e1 = ev(), ev()
             e0.record(); flat[:half].copy_(flat[half:2 * half]); e1.record(); torch.cuda.synchronize()
             print("torch copy %.3f ms %.1f GB/s (r+w)" % (e0.elapsed_time(e1), half * 16 / e0.elapsed_time(e1) / 1e6))
+    for rep in range(4):
+        e0, e1 = ev(), ev()
+        e0.record(); prob.solve(y0, n0, T, out, 1); e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        print("SOLVE (K1+K1b+K2) %.3f ms  %.3e mode-steps/s" % (ms, steps / ms * 1e3))
     prob.check_flags()
     print("T", T, "nk", nk, "tsix", m.fotstartindex.min(), m.fotstartindex.max())
 

@@ -194,6 +194,28 @@ def test_windowed_host_path_is_bitwise_identical():
     assert np.array_equal(every.view(np.float64), full[::7].view(np.float64), equal_nan=True)
 
 
+def test_fused_solve_equals_separate_kernels():
+    """pf_fo_solve (producer CTA + consumers in one launch, nf = 1) against the three-kernel
+    sequence pf_bg_run / pf_stage_table / pf_fo_run, and its windowed continuation."""
+    import torch
+    from pyflation_b200 import engine
+    g = load_fo("c2_lambdaphi4_2p16")
+    m, prob = _problem(g, k=np.linspace(KMIN, KMAX, 5000))
+    y0 = np.real(m.foystart[0:3, 0])
+    n0 = int(m.fotstartindex.min())
+    separate = engine.first_order_device(prob).cpu().numpy()
+    pm = engine.make_model(m.potential_func, m.pot_params, 1, m.ainit)
+    for rep in range(3):                                  # repeat: the ticket / progress words are reused
+        prob2 = engine.FirstOrderProblem(pm, m.k, m.fotstartindex, m.foystart, 0.0, prob.T, 0.01)
+        fused = engine.first_order_device(prob2, y0=y0, n0=n0).cpu().numpy()
+        prob2.check_flags()
+        assert rel_err(fused[:, :3], separate[:, :3]) < 1e-13
+        assert mode_rel_err(fused, separate, 1) < 1e-12
+    prob3 = engine.FirstOrderProblem(pm, m.k, m.fotstartindex, m.foystart, 0.0, prob.T, 0.01)
+    host = engine.first_order_host(prob3, slab_bytes=64 << 20, y0=y0, n0=n0).numpy()
+    assert np.array_equal(host.view(np.float64), fused.view(np.float64), equal_nan=True)
+
+
 def test_linearity_and_column_independence():
     """The perturbation equations are linear with real coefficients: scaling a column's start
     vector by 4 (exact in binary) scales its trajectory by 4 bit-for-bit; a column's result
