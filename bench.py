@@ -377,8 +377,13 @@ def run_e2e(args, m, T, nvar, mode_steps, world, rank, barrier):
         last = host[T - 1].numpy()
         assert np.isfinite(last[3:]).all()
     h2d = int(ystart_host.size * 16 + m.k.size * 8 + tsix_host.size * 8)
+    # full layout: every row crosses PCIe; compact (default when the host can hold the result):
+    # the 2 perturbation rows of every time step + the 1 MB step-record table cross, the 3
+    # background rows are rebuilt on the host by pf_host_fill_background
+    d2h = int(need) if not full else int(T * 2 * NK_PER_GPU * 16 + T * 16 * 8)
     return {"value": float(ww[0]) * nsteps / float(tt[0]), "unit": UNIT,
-            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(need), "steps": nsteps,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "host_result_bytes_per_step": int(need), "steps": nsteps,
             "ms_per_step": 1e3 * float(tt[0]) / nsteps,
             "host_buffer": "full pinned yresult" if full else "pinned ring (host RAM too small for N full results)",
             "api": "rk4.rkdriver_tsix(ystart, simtstart, tsix, tend, h, derivs=CanonicalFirstOrder.derivs, "

@@ -80,6 +80,12 @@ typedef struct pf_model {
     double ainit;                     /* a(t) = ainit * exp(t); unused by pf_bg_run */
 } pf_model;
 
+/* output layouts of pf_fo_run / pf_fo_solve */
+#define PF_LAYOUT_FULL 0        /* every row of yresult: [rows][nvar][nk] */
+#define PF_LAYOUT_PERT 1        /* perturbation rows only: [rows][2 nf^2][nk]; the background rows
+                                   are identical for every mode, so a host-bound result ships
+                                   them once (pf_host_fill_background) instead of nk times */
+
 /* flags written by pf_fo_run into *flags_dev (bitwise OR) */
 #define PF_FLAG_BG_MISMATCH 1   /* a column's ystart background rows are not on column 0's trajectory */
 
@@ -133,7 +139,7 @@ int pf_stage_table(const pf_model *m, int64_t T, double simtstart, double h, int
 int pf_fo_run(const pf_model *m, int64_t nk, const double *k_dev, const int64_t *tsix_dev,
               const double *ystart_dev, const double *rec_dev, int64_t T, double h,
               int64_t t0, int64_t t1, double *state_dev, double *yout_dev, int64_t out_every,
-              int32_t *flags_dev, void *stream);
+              int32_t layout, int32_t *flags_dev, void *stream);
 
 /* ---- one-call solve of the first window [0, t1): K1 + K1b + K2 ----
  * What rk4.rkdriver_tsix does for a CanonicalFirstOrder model in one call.  For single-field
@@ -150,13 +156,27 @@ int64_t pf_solve_scratch_doubles(int nfields, int64_t T);
 int pf_fo_solve(const pf_model *m, int64_t nk, const double *k_dev, const int64_t *tsix_dev,
                 const double *ystart_dev, int64_t n0, const double *y0_host, int64_t T,
                 double simtstart, double h, int64_t t1, double *scratch_dev, double *state_dev,
-                double *yout_dev, int64_t out_every, int32_t *ws_dev, void *stream);
+                double *yout_dev, int64_t out_every, int32_t layout, int32_t *ws_dev, void *stream);
 
 /* ---- K5: curvature power spectrum of trajectory rows (adiabatic.py:153-285) ----
  * y_dev c128 [nrows][nvar][nk] -> Pr_dev [nrows][nk];  if k_dev != NULL the result is the
  * scaled spectrum k^3/(2 pi^2) P_R (utilities.py:12-37). */
 int pf_pr_spectrum(int nfields, int64_t nrows, int64_t nk, const double *y_dev,
                    const double *k_dev, double *Pr_dev, void *stream);
+
+/* ---- host-bound results: ship the perturbation rows over PCIe, rebuild the rest on the host ----
+ * pf_copy_rows_d2h: asynchronous 2-D device->host copy (height rows of width_bytes each, with
+ * pitches), used to drop a PF_LAYOUT_PERT window into rows [2nf+1, nvar) of the host yresult.
+ * pf_host_fill_background: host threads write rows [0, 2nf+1) of yresult[t0:t1] -- NaN+NaNj
+ * before a mode's start row, ystart[:,k] at it (bit for bit, rk4.py:106-107), (bg[t][v], 0)
+ * after it.  bg_host is [T][bg_pitch] doubles with the background row at column bg_off
+ * (pass the step records: bg_pitch = pf_rec_doubles(nf), bg_off = 4(2+nf^2)).  Streaming
+ * (non-temporal) stores; nthreads <= 0 picks the hardware concurrency. */
+int pf_copy_rows_d2h(void *dst_host, size_t dst_pitch, const void *src_dev, size_t src_pitch,
+                     size_t width_bytes, size_t height, void *stream);
+int pf_host_fill_background(double *yout_host, int nfields, int64_t nk, int64_t t0, int64_t t1,
+                            const double *bg_host, int64_t bg_pitch, int64_t bg_off,
+                            const int64_t *tsix_host, const double *ystart_host, int nthreads);
 
 /* ---- gather helper for the k-sharded multi-GPU layout ----
  * Interleave a rank's slab [nrows][nvar][nk_r] into the global layout [nrows][nvar][nk] at

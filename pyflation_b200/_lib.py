@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("PYFLATION_B200_LIB", os.path.join(_HERE, "lib", "libp
 PF_MAX_NFIELDS = 8
 PF_MAX_PARAMS = 8
 PF_FLAG_BG_MISMATCH = 1
+PF_LAYOUT_FULL, PF_LAYOUT_PERT = 0, 1
 
 # names every build must export (checked by tests/test_abi.py against the header)
 EXPORTS = [
@@ -20,7 +21,8 @@ EXPORTS = [
     "pf_potential_nfields", "pf_potential_nparams", "pf_potential_param_name",
     "pf_potential_param_default", "pf_potential_eval", "pf_number_of_steps", "pf_nvar",
     "pf_rec_doubles", "pf_bg_run", "pf_stage_table", "pf_fo_run", "pf_solve_scratch_doubles",
-    "pf_fo_solve", "pf_pr_spectrum", "pf_scatter_slab",
+    "pf_fo_solve", "pf_pr_spectrum", "pf_scatter_slab", "pf_copy_rows_d2h",
+    "pf_host_fill_background",
 ]
 
 
@@ -80,11 +82,15 @@ def lib():
     L.pf_bg_run.argtypes = [mp, c_i64, c_dbl, c_i64, ctypes.POINTER(c_dbl), c_vp, c_vp, c_vp]
     L.pf_stage_table.argtypes = [mp, c_i64, c_dbl, c_dbl, c_i64, c_vp, c_vp, c_vp, c_vp]
     L.pf_fo_run.argtypes = [mp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_dbl, c_i64, c_i64,
-                            c_vp, c_vp, c_i64, c_vp, c_vp]
+                            c_vp, c_vp, c_i64, ctypes.c_int32, c_vp, c_vp]
     L.pf_solve_scratch_doubles.argtypes = [c_int, c_i64]
     L.pf_solve_scratch_doubles.restype = c_i64
     L.pf_fo_solve.argtypes = [mp, c_i64, c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(c_dbl), c_i64, c_dbl,
-                              c_dbl, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]
+                              c_dbl, c_i64, c_vp, c_vp, c_vp, c_i64, ctypes.c_int32, c_vp, c_vp]
+    c_sz = ctypes.c_size_t
+    L.pf_copy_rows_d2h.argtypes = [c_vp, c_sz, c_vp, c_sz, c_sz, c_sz, c_vp]
+    L.pf_host_fill_background.argtypes = [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64,
+                                          c_vp, c_vp, c_int]
     L.pf_pr_spectrum.argtypes = [c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]
     L.pf_scatter_slab.argtypes = [c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]
     _lib = L

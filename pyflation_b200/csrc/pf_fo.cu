@@ -77,7 +77,10 @@ __device__ __forceinline__ void mode_rhs(const double* __restrict__ cs, double k
 template <int NF, int NC>
 __global__ void __launch_bounds__(FoShape<NF>::BLOCK) fo_rk4_kernel(FoArgs a) {
     using S = FoShape<NF>;
-    constexpr int NB = S::NB, SW = S::SW, REC = S::REC, CH = S::CH, NV = nvar_of(NF);
+    constexpr int NB = S::NB, SW = S::SW, REC = S::REC, CH = S::CH;
+    const bool pert = a.layout == PF_LAYOUT_PERT;     // perturbation rows only
+    const int NV = pert ? 2 * NF * NF : nvar_of(NF);
+    const int RO = pert ? -NB : 0;                    // row offset of the perturbation block
     constexpr int KPB = S::BLOCK / (3 - NC);        // k modes per CTA
 
     __shared__ __align__(128) double srec[2][CH * REC];
@@ -153,12 +156,14 @@ __global__ void __launch_bounds__(FoShape<NF>::BLOCK) fo_rk4_kernel(FoArgs a) {
                     double nn[NC];
 #pragma unroll
                     for (int cc = 0; cc < NC; ++cc) nn[cc] = nan;
-                    store_row<NC>(orow + 2 * (int64_t)(2 * j) * nk, kk, part, nn);
-                    store_row<NC>(orow + 2 * (int64_t)(2 * j + 1) * nk, kk, part, nn);
-                    if (j == 0) store_row<NC>(orow + 2 * (int64_t)(2 * NF) * nk, kk, part, nn);
+                    if (!pert) {
+                        store_row<NC>(orow + 2 * (int64_t)(2 * j) * nk, kk, part, nn);
+                        store_row<NC>(orow + 2 * (int64_t)(2 * j + 1) * nk, kk, part, nn);
+                        if (j == 0) store_row<NC>(orow + 2 * (int64_t)(2 * NF) * nk, kk, part, nn);
+                    }
 #pragma unroll
                     for (int i = 0; i < NF; ++i) {
-                        const int64_t row = NB + 2 * (i * NF + j);
+                        const int64_t row = RO + NB + 2 * (i * NF + j);
                         store_row<NC>(orow + 2 * row * nk, kk, part, nn);
                         store_row<NC>(orow + 2 * (row + 1) * nk, kk, part, nn);
                     }
@@ -200,12 +205,14 @@ __global__ void __launch_bounds__(FoShape<NF>::BLOCK) fo_rk4_kernel(FoArgs a) {
                     }
                 }
                 if (out) {
-                    store_row<NC>(orow + 2 * (int64_t)(2 * j) * nk, kk, part, bgv[0]);
-                    store_row<NC>(orow + 2 * (int64_t)(2 * j + 1) * nk, kk, part, bgv[1]);
-                    if (j == 0) store_row<NC>(orow + 2 * (int64_t)(2 * NF) * nk, kk, part, bgv[2]);
+                    if (!pert) {
+                        store_row<NC>(orow + 2 * (int64_t)(2 * j) * nk, kk, part, bgv[0]);
+                        store_row<NC>(orow + 2 * (int64_t)(2 * j + 1) * nk, kk, part, bgv[1]);
+                        if (j == 0) store_row<NC>(orow + 2 * (int64_t)(2 * NF) * nk, kk, part, bgv[2]);
+                    }
 #pragma unroll
                     for (int i = 0; i < NF; ++i) {
-                        const int64_t row = NB + 2 * (i * NF + j);
+                        const int64_t row = RO + NB + 2 * (i * NF + j);
                         store_row<NC>(orow + 2 * row * nk, kk, part, x[i]);
                         store_row<NC>(orow + 2 * (row + 1) * nk, kk, part, v[i]);
                     }
@@ -289,7 +296,7 @@ using namespace pf;
 extern "C" int pf_fo_run(const pf_model* m, int64_t nk, const double* k_dev, const int64_t* tsix_dev,
                          const double* ystart_dev, const double* rec_dev, int64_t T, double h,
                          int64_t t0, int64_t t1, double* state_dev, double* yout_dev,
-                         int64_t out_every, int32_t* flags_dev, void* stream) {
+                         int64_t out_every, int32_t layout, int32_t* flags_dev, void* stream) {
     int rc = check_model(m);
     if (rc) return rc;
     if (nk < 0 || T < 1 || t0 < 0 || t1 > T || t0 > t1 || out_every < 0) {
@@ -302,7 +309,9 @@ extern "C" int pf_fo_run(const pf_model* m, int64_t nk, const double* k_dev, con
     if (!k_dev || !tsix_dev || !ystart_dev || !rec_dev) { set_error("pf_fo_run: null buffer"); return PF_E_ARG; }
     if (t0 > 0 && !state_dev) { set_error("pf_fo_run: a window with t0 > 0 needs state_dev"); return PF_E_ARG; }
     if (out_every > 0 && !yout_dev) { set_error("pf_fo_run: out_every > 0 needs yout_dev"); return PF_E_ARG; }
+    if (layout != PF_LAYOUT_FULL && layout != PF_LAYOUT_PERT) { set_error("pf_fo_run: unknown layout %d", layout); return PF_E_ARG; }
     FoArgs a;
+    a.layout = layout;
     a.nk = nk; a.k = k_dev; a.tsix = tsix_dev; a.ystart = ystart_dev; a.rec = rec_dev;
     a.T = T; a.t0 = t0; a.t1 = t1; a.state = state_dev;
     a.yout = out_every > 0 ? yout_dev : nullptr; a.out_every = out_every; a.flags = flags_dev;
@@ -335,8 +344,8 @@ extern "C" int64_t pf_solve_scratch_doubles(int nfields, int64_t T) {
 extern "C" int pf_fo_solve(const pf_model* m, int64_t nk, const double* k_dev, const int64_t* tsix_dev,
                            const double* ystart_dev, int64_t n0, const double* y0_host, int64_t T,
                            double simtstart, double h, int64_t t1, double* scratch_dev,
-                           double* state_dev, double* yout_dev, int64_t out_every, int32_t* ws_dev,
-                           void* stream) {
+                           double* state_dev, double* yout_dev, int64_t out_every, int32_t layout,
+                           int32_t* ws_dev, void* stream) {
     int rc = check_model(m);
     if (rc) return rc;
     if (nk < 0 || T < 1 || t1 < 0 || t1 > T || out_every < 0) { set_error("pf_fo_solve: bad sizes"); return PF_E_ARG; }
@@ -345,6 +354,7 @@ extern "C" int pf_fo_solve(const pf_model* m, int64_t nk, const double* k_dev, c
     if (!y0_host || !scratch_dev || !ws_dev) { set_error("pf_fo_solve: null buffer"); return PF_E_ARG; }
     if (nk > 0 && (!k_dev || !tsix_dev || !ystart_dev)) { set_error("pf_fo_solve: null buffer"); return PF_E_ARG; }
     if (out_every > 0 && !yout_dev) { set_error("pf_fo_solve: out_every > 0 needs yout_dev"); return PF_E_ARG; }
+    if (layout != PF_LAYOUT_FULL && layout != PF_LAYOUT_PERT) { set_error("pf_fo_solve: unknown layout %d", layout); return PF_E_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     const int nf = m->nfields;
     double* rec = scratch_dev;
@@ -356,7 +366,7 @@ extern "C" int pf_fo_solve(const pf_model* m, int64_t nk, const double* k_dev, c
         FoArgs a;
         a.nk = nk; a.k = k_dev; a.tsix = tsix_dev; a.ystart = ystart_dev; a.rec = rec;
         a.T = T; a.t0 = 0; a.t1 = t1; a.state = state_dev; a.yout = yout_dev; a.out_every = 1;
-        a.flags = ws_dev + 1; a.h = h;
+        a.flags = ws_dev + 1; a.h = h; a.layout = layout;
         if (launch_fo1_fused(m, a, simtstart, n0, y0_host, rec, ws_dev, st)) {
             PF_CUDA_CHECK(cudaGetLastError(), "pf_fo_solve fused launch");
             return PF_OK;
@@ -367,5 +377,5 @@ extern "C" int pf_fo_solve(const pf_model* m, int64_t nk, const double* k_dev, c
     rc = pf_stage_table(m, T, simtstart, h, n0, bg, stagey, rec, stream);
     if (rc) return rc;
     return pf_fo_run(m, nk, k_dev, tsix_dev, ystart_dev, rec, T, h, 0, t1, state_dev, yout_dev, out_every,
-                     ws_dev + 1, stream);
+                     layout, ws_dev + 1, stream);
 }

@@ -83,9 +83,11 @@ __device__ __forceinline__ void wait_progress(const long long* progress, long lo
 
 // Consumer: integrates the modes of logical CTA `cta` (nthreads threads, KPT modes each).
 // `progress` (may be null) is the producer's published record count in fused launches.
-template <int KPT>
+template <int KPT, bool PERT>
 __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nthreads,
                                             const long long* progress) {
+    constexpr int NV = PERT ? 2 : 5;                  // rows per time step in the output
+    constexpr int XO = PERT ? 0 : 3;                  // row of dphi within a time step
     __shared__ __align__(128) double srec[2][FO1_CH * FO1_REC];
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ long long s_tsmin, s_tsmax;
@@ -130,7 +132,7 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
     const double h = a.h, hh = h * 0.5, h6 = h / 6.0;         // rk4.py:31-32
     const double nan = qnan();
     double2* prow = reinterpret_cast<double2*>(a.yout) + kk0; // row t0, var 0, this thread's k
-    const int64_t rstride = 5 * nk;
+    const int64_t rstride = NV * nk;
 
     // ---- regime 1: rows before any mode of this CTA starts: NaN+NaNj, no records needed
     int64_t n = a.t0;
@@ -140,7 +142,7 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
         for (int m = 0; m < KPT; ++m)
             if (live[m]) {
 #pragma unroll
-                for (int var = 0; var < 5; ++var) __stcs(prow + var * nk + m, make_double2(nan, nan));
+                for (int var = 0; var < NV; ++var) __stcs(prow + var * nk + m, make_double2(nan, nan));
             }
         prow += rstride;
     }
@@ -176,11 +178,13 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
 #pragma unroll
                 for (int m = 0; m < KPT; ++m)
                     if (live[m]) {
-                        __stcs(prow + m, make_double2(cf.bg[0], 0.0));
-                        __stcs(prow + nk + m, make_double2(cf.bg[1], 0.0));
-                        __stcs(prow + 2 * nk + m, make_double2(cf.bg[2], 0.0));
-                        __stcs(prow + 3 * nk + m, make_double2(x[m][0], x[m][1]));
-                        __stcs(prow + 4 * nk + m, make_double2(v[m][0], v[m][1]));
+                        if constexpr (!PERT) {
+                            __stcs(prow + m, make_double2(cf.bg[0], 0.0));
+                            __stcs(prow + nk + m, make_double2(cf.bg[1], 0.0));
+                            __stcs(prow + 2 * nk + m, make_double2(cf.bg[2], 0.0));
+                        }
+                        __stcs(prow + XO * nk + m, make_double2(x[m][0], x[m][1]));
+                        __stcs(prow + (XO + 1) * nk + m, make_double2(v[m][0], v[m][1]));
                     }
                 if (n + 1 < a.T) {
 #pragma unroll
@@ -193,7 +197,7 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
                     if (!live[m]) continue;
                     if (n < ts[m]) {
 #pragma unroll
-                        for (int var = 0; var < 5; ++var)
+                        for (int var = 0; var < NV; ++var)
                             __stcs(prow + var * nk + m, make_double2(nan, nan));   // rk4.py:100
                         continue;
                     }
@@ -212,11 +216,13 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
                             if (bad) atomicOr(a.flags, PF_FLAG_BG_MISMATCH);
                         }
                     }
-                    __stcs(prow + m, b0);
-                    __stcs(prow + nk + m, b1);
-                    __stcs(prow + 2 * nk + m, b2);
-                    __stcs(prow + 3 * nk + m, make_double2(x[m][0], x[m][1]));
-                    __stcs(prow + 4 * nk + m, make_double2(v[m][0], v[m][1]));
+                    if constexpr (!PERT) {
+                        __stcs(prow + m, b0);
+                        __stcs(prow + nk + m, b1);
+                        __stcs(prow + 2 * nk + m, b2);
+                    }
+                    __stcs(prow + XO * nk + m, make_double2(x[m][0], x[m][1]));
+                    __stcs(prow + (XO + 1) * nk + m, make_double2(v[m][0], v[m][1]));
                     if (n + 1 < a.T) rk4_mode(cf, kval[m], h, hh, h6, x[m], v[m]);
                 }
             }
@@ -236,9 +242,9 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
     }
 }
 
-template <int KPT>
+template <bool PERT>
 __global__ void __launch_bounds__(512) fo1_kernel(FoArgs a) {
-    fo1_consume<KPT>(a, blockIdx.x, blockDim.x, nullptr);
+    fo1_consume<1, PERT>(a, blockIdx.x, blockDim.x, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -366,7 +372,9 @@ __global__ void __launch_bounds__(512) fo1_fused_kernel(FoArgs a, ProdArgs f, in
         fo1_produce<POT>(a, f);
         return;
     }
-    fo1_consume<1>(a, cta - 1, cthreads, reinterpret_cast<const long long*>(f.ws + 2));
+    const long long* progress = reinterpret_cast<const long long*>(f.ws + 2);
+    if (a.layout == PF_LAYOUT_PERT) fo1_consume<1, true>(a, cta - 1, cthreads, progress);
+    else fo1_consume<1, false>(a, cta - 1, cthreads, progress);
 }
 
 // Grid shape: a whole number c of CTAs per SM, c the smallest for which a CTA holds at most
@@ -399,7 +407,8 @@ static int64_t fo1_block(int64_t nk, int sms) {
 int launch_fo1(const FoArgs& a, cudaStream_t st) {
     const int64_t block = fo1_block(a.nk, sm_count());
     const int64_t grid = (a.nk + block - 1) / block;
-    fo1_kernel<1><<<(unsigned)grid, (unsigned)block, 0, st>>>(a);
+    if (a.layout == PF_LAYOUT_PERT) fo1_kernel<true><<<(unsigned)grid, (unsigned)block, 0, st>>>(a);
+    else fo1_kernel<false><<<(unsigned)grid, (unsigned)block, 0, st>>>(a);
     return 0;
 }
 

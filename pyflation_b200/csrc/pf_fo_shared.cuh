@@ -16,6 +16,7 @@ struct FoArgs {
     int64_t out_every;
     int32_t* flags;
     double h;
+    int32_t layout;                      // PF_LAYOUT_FULL or PF_LAYOUT_PERT
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

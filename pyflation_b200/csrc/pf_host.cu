@@ -1,0 +1,92 @@
+// Host-side half of a host-bound solve (see PF_LAYOUT_PERT in include/pyflation_b200.h):
+// the PCIe link carries only the perturbation rows; the background rows, identical for every
+// mode, and the NaN prefix are written straight into the caller's yresult by host threads
+// with non-temporal stores while the device->host copies are in flight.
+#include <emmintrin.h>
+#include <math.h>
+
+#include <thread>
+#include <vector>
+
+#include "pf_common.cuh"
+
+namespace pf {
+
+// One time step at a time: the start-row test is done once per mode and feeds all 2nf+1
+// background rows (2nf+1 independent non-temporal store streams).
+template <int NB>
+static void fill_rows_nb(double* yout, int nvar, int64_t nk, int64_t ta, int64_t tb, const double* bg,
+                         int64_t bg_pitch, int64_t bg_off, const int64_t* tsix, const double* ystart) {
+    const __m128d nan2 = _mm_set1_pd(NAN);
+    for (int64_t t = ta; t < tb; ++t) {
+        __m128d val[NB];
+        double* row[NB];
+        for (int v = 0; v < NB; ++v) {
+            val[v] = _mm_set_pd(0.0, bg[t * bg_pitch + bg_off + v]);              // (re, im = 0)
+            row[v] = yout + 2 * ((t * nvar + v) * nk);
+        }
+        for (int64_t k = 0; k < nk; ++k) {
+            const int64_t s = tsix[k];
+            if (t > s) {
+                for (int v = 0; v < NB; ++v) _mm_stream_pd(row[v] + 2 * k, val[v]);
+            } else if (t < s) {
+                for (int v = 0; v < NB; ++v) _mm_stream_pd(row[v] + 2 * k, nan2);
+            } else {                                                             // rk4.py:106-107
+                for (int v = 0; v < NB; ++v)
+                    _mm_stream_pd(row[v] + 2 * k, _mm_loadu_pd(ystart + 2 * ((int64_t)v * nk + k)));
+            }
+        }
+    }
+    _mm_sfence();
+}
+
+static void fill_rows(double* yout, int nb, int nvar, int64_t nk, int64_t ta, int64_t tb,
+                      const double* bg, int64_t bg_pitch, int64_t bg_off, const int64_t* tsix,
+                      const double* ystart) {
+    switch (nb) {
+#define PF_CASE(N) case N: fill_rows_nb<N>(yout, nvar, nk, ta, tb, bg, bg_pitch, bg_off, tsix, ystart); break;
+        PF_CASE(3) PF_CASE(5) PF_CASE(7) PF_CASE(9) PF_CASE(11) PF_CASE(13) PF_CASE(15) PF_CASE(17)
+#undef PF_CASE
+        default: break;
+    }
+}
+
+}  // namespace pf
+
+using namespace pf;
+
+extern "C" int pf_copy_rows_d2h(void* dst_host, size_t dst_pitch, const void* src_dev, size_t src_pitch,
+                                size_t width_bytes, size_t height, void* stream) {
+    if (height == 0 || width_bytes == 0) return PF_OK;
+    if (!dst_host || !src_dev || dst_pitch < width_bytes || src_pitch < width_bytes) {
+        set_error("pf_copy_rows_d2h: bad arguments");
+        return PF_E_ARG;
+    }
+    PF_CUDA_CHECK(cudaMemcpy2DAsync(dst_host, dst_pitch, src_dev, src_pitch, width_bytes, height,
+                                    cudaMemcpyDeviceToHost, (cudaStream_t)stream),
+                  "pf_copy_rows_d2h");
+    return PF_OK;
+}
+
+extern "C" int pf_host_fill_background(double* yout_host, int nfields, int64_t nk, int64_t t0, int64_t t1,
+                                       const double* bg_host, int64_t bg_pitch, int64_t bg_off,
+                                       const int64_t* tsix_host, const double* ystart_host, int nthreads) {
+    if (nfields < 1 || nfields > PF_MAX_NFIELDS) { set_error("pf_host_fill_background: nfields=%d", nfields); return PF_E_NFIELDS; }
+    if (nk < 0 || t0 < 0 || t1 < t0) { set_error("pf_host_fill_background: bad sizes"); return PF_E_ARG; }
+    if (nk == 0 || t0 == t1) return PF_OK;
+    if (!yout_host || !bg_host || !tsix_host || !ystart_host) { set_error("pf_host_fill_background: null buffer"); return PF_E_ARG; }
+    if (((uintptr_t)yout_host & 15) != 0) { set_error("pf_host_fill_background: yresult must be 16-byte aligned"); return PF_E_ARG; }
+    const int nb = nbg_of(nfields), nvar = nvar_of(nfields);
+    int nt = nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    const int64_t rows = t1 - t0;
+    if (nt > rows) nt = (int)rows;
+    std::vector<std::thread> pool;
+    for (int w = 0; w < nt; ++w) {
+        const int64_t ta = t0 + rows * w / nt, tb = t0 + rows * (w + 1) / nt;
+        pool.emplace_back(fill_rows, yout_host, nb, nvar, nk, ta, tb, bg_host, bg_pitch, bg_off, tsix_host,
+                          ystart_host);
+    }
+    for (auto& th : pool) th.join();
+    return PF_OK;
+}

@@ -12,6 +12,7 @@ rk4.py:58-138, for a ``CanonicalFirstOrder.derivs``):
                                               to (pinned) host memory while the next computes
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -107,6 +108,10 @@ class FirstOrderProblem(object):
         self.k = as_dev(k, torch.float64)
         self.tsix = as_dev(tsix, torch.int64)
         self.ystart = as_dev(ystart, torch.complex128)
+        # host copies, used when the result is delivered to host memory (background fill)
+        self.tsix_host = None if torch.is_tensor(tsix) else np.ascontiguousarray(tsix, dtype=np.int64)
+        self.ystart_host = None if torch.is_tensor(ystart) else \
+            np.ascontiguousarray(ystart, dtype=np.complex128)
         if tuple(self.ystart.shape) != (self.nvar, self.nk):
             raise ValueError("ystart must have shape (%d, %d)" % (self.nvar, self.nk))
         self.ws = torch.zeros(8, dtype=torch.int32, device=self.dev)    # [1] = PF_FLAG_* bits
@@ -121,7 +126,7 @@ class FirstOrderProblem(object):
         self.bg, self.rec = background_tables(self.model, y0, self.T, self.h, self.simtstart,
                                               n0, True, self.dev)
 
-    def solve(self, y0, n0, t1, yout, out_every=1, stream=None):
+    def solve(self, y0, n0, t1, yout, out_every=1, stream=None, layout=0):
         """pf_fo_solve: K1 + K1b + K2 for the window [0, t1) -- one fused launch for single-field
         full-trajectory runs.  Leaves the step records in ``self.rec`` for later windows."""
         L = _lib.lib()
@@ -138,18 +143,18 @@ class FirstOrderProblem(object):
                                      y0.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), self.T,
                                      self.simtstart, self.h, int(t1), _ptr(self.scratch),
                                      _ptr(self.state), _ptr(yout),
-                                     int(out_every if yout is not None else 0), _ptr(self.ws),
-                                     _stream_ptr(stream)))
+                                     int(out_every if yout is not None else 0), int(layout),
+                                     _ptr(self.ws), _stream_ptr(stream)))
         nrec = int(L.pf_rec_doubles(nf))
         self.rec = self.scratch[:self.T * nrec].view(self.T, nrec)
 
-    def launch(self, t0, t1, yout, out_every=1, stream=None):
+    def launch(self, t0, t1, yout, out_every=1, stream=None, layout=0):
         """K2: rows [t0, t1) -> yout (device c128 tensor or None)."""
         L = _lib.lib()
         _lib.check(L.pf_fo_run(ctypes.byref(self.model), self.nk, _ptr(self.k), _ptr(self.tsix),
                                _ptr(self.ystart), _ptr(self.rec), self.T, self.h, int(t0), int(t1),
                                _ptr(self.state), _ptr(yout), int(out_every if yout is not None else 0),
-                               _ptr(self.flags), _stream_ptr(stream)))
+                               int(layout), _ptr(self.flags), _stream_ptr(stream)))
 
     def check_flags(self):
         f = int(self.flags.item())
@@ -188,15 +193,29 @@ def plan_window(T, nvar, nk, slab_bytes):
     return rows
 
 
-def first_order_host(prob, out=None, slab_bytes=1 << 30, ring=None, y0=None, n0=None):
-    """Trajectory delivered into host memory: time windows ping-pong between two device slabs;
+def first_order_host(prob, out=None, slab_bytes=1 << 30, ring=None, y0=None, n0=None, compact=True,
+                     fill_threads=0):
+    """Trajectory delivered into host memory.  Time windows ping-pong between two device slabs;
     the device->host copy of window w overlaps the integration of window w+1.
-    Returns a torch CPU tensor (T, nvar, nk) complex128 (pinned when it could be).
 
+    compact (default): the kernels write only the perturbation rows (PF_LAYOUT_PERT) and only
+    those cross PCIe (2-D copies straight into rows [2nf+1, nvar) of the result); the
+    background rows -- the same numbers for every mode -- and the NaN prefix are written into
+    the result by host threads (pf_host_fill_background) from the 1 MB step-record table,
+    concurrently with the copies.  For nf=1 that is 40 % of the bytes on the link.
+
+    Returns a torch CPU tensor (T, nvar, nk) complex128 (pinned when it could be).
     ``ring``: a (R, nvar, nk) host tensor used instead of a full-size result when host memory
     cannot hold it -- every row still crosses to the host, windows overwrite each other."""
-    T, nvar, nk = prob.T, prob.nvar, prob.nk
-    W = plan_window(T, nvar, nk, slab_bytes)
+    import threading
+    L = _lib.lib()
+    T, nvar, nk, nf = prob.T, prob.nvar, prob.nk, prob.nf
+    nb = 2 * nf + 1
+    npert = nvar - nb
+    compact = bool(compact and ring is None and prob.tsix_host is not None
+                   and prob.ystart_host is not None)
+    rows_per_t = npert if compact else nvar
+    W = plan_window(T, rows_per_t, nk, slab_bytes)
     if ring is not None:
         W = max(1, min(W, ring.shape[0] // 2))
     elif out is None:
@@ -204,8 +223,11 @@ def first_order_host(prob, out=None, slab_bytes=1 << 30, ring=None, y0=None, n0=
     elif tuple(out.shape) != (T, nvar, nk) or out.dtype != torch.complex128 or not out.is_contiguous():
         raise ValueError("output buffer must be a contiguous complex128 tensor of shape %r"
                          % ((T, nvar, nk),))
+    layout = _lib.PF_LAYOUT_PERT if compact else _lib.PF_LAYOUT_FULL
+    filler = None
+    fill_rc = []
     with torch.cuda.device(prob.dev):
-        slabs = [torch.empty((W, nvar, nk), dtype=torch.complex128, device=prob.dev)
+        slabs = [torch.empty((W, rows_per_t, nk), dtype=torch.complex128, device=prob.dev)
                  for _ in range(2 if W < T else 1)]
         compute = torch.cuda.current_stream()
         copier = torch.cuda.Stream()
@@ -217,21 +239,46 @@ def first_order_host(prob, out=None, slab_bytes=1 << 30, ring=None, y0=None, n0=
             if copied[b] is not None:
                 compute.wait_event(copied[b])           # slab b is free again
             if t0 == 0 and y0 is not None:
-                prob.solve(y0, n0, t1, slabs[b], 1, compute)     # K1 + K1b ride along
+                prob.solve(y0, n0, t1, slabs[b], 1, compute, layout)   # K1 + K1b ride along
             else:
-                prob.launch(t0, t1, slabs[b], 1, compute)
+                prob.launch(t0, t1, slabs[b], 1, compute, layout)
             done = torch.cuda.Event()
             done.record(compute)
             copier.wait_event(done)
             with torch.cuda.stream(copier):
-                dst = out[t0:t1] if ring is None else ring[(w % 2) * W:(w % 2) * W + (t1 - t0)]
-                dst.copy_(slabs[b][:t1 - t0], non_blocking=True)
+                if compact:
+                    dst = out.data_ptr() + (t0 * nvar + nb) * nk * 16
+                    _lib.check(L.pf_copy_rows_d2h(ctypes.c_void_p(dst), nvar * nk * 16, _ptr(slabs[b]),
+                                                  npert * nk * 16, npert * nk * 16, t1 - t0,
+                                                  _stream_ptr(copier)))
+                else:
+                    dst = out[t0:t1] if ring is None else ring[(w % 2) * W:(w % 2) * W + (t1 - t0)]
+                    dst.copy_(slabs[b][:t1 - t0], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copier)
             copied[b] = ev
+            if compact and t0 == 0 and not os.environ.get("PF_E2E_NOFILL"):
+                # the step records (background rows included) are complete once window 0 is:
+                # bring them over and let the host threads write the background rows of every
+                # time step while the remaining windows compute and copy
+                rec_host = prob.rec.cpu().numpy()
+                bg_off = 4 * (2 + nf * nf)
+                nthreads = fill_threads or len(os.sched_getaffinity(0))
+
+                def _fill():
+                    fill_rc.append(L.pf_host_fill_background(
+                        ctypes.c_void_p(out.data_ptr()), nf, nk, 0, T,
+                        ctypes.c_void_p(rec_host.ctypes.data), rec_host.shape[1], bg_off,
+                        ctypes.c_void_p(prob.tsix_host.ctypes.data),
+                        ctypes.c_void_p(prob.ystart_host.ctypes.data), nthreads))
+                filler = threading.Thread(target=_fill)
+                filler.start()
             w += 1
         copier.synchronize()
         compute.synchronize()
+    if filler is not None:
+        filler.join()
+        _lib.check(fill_rc[0])
     return out if ring is None else ring
 
 
