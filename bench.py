@@ -212,6 +212,8 @@ def run_gpu_arm(args):
         cpu_baseline = {"value": work / wall, "unit": UNIT, "cores": arm.cores, "kind": "port",
                         "sample": arm.sample, "wall_s": wall}
 
+    if os.environ.get("NCCL_DEBUG", "VERSION") == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
@@ -382,8 +384,8 @@ def run_e2e(args, m, T, nvar, mode_steps, world, rank, barrier):
     # background rows are rebuilt on the host by pf_host_fill_background
     d2h = int(need) if not full else int(T * 2 * NK_PER_GPU * 16 + T * 16 * 8)
     return {"value": float(ww[0]) * nsteps / float(tt[0]), "unit": UNIT,
-            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "host_result_bytes_per_step": int(need), "steps": nsteps,
+            "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+            "host_result_bytes_per_step": int(need) * world, "steps": nsteps,
             "ms_per_step": 1e3 * float(tt[0]) / nsteps,
             "host_buffer": "full pinned yresult" if full else "pinned ring (host RAM too small for N full results)",
             "api": "rk4.rkdriver_tsix(ystart, simtstart, tsix, tend, h, derivs=CanonicalFirstOrder.derivs, "
