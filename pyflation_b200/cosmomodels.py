@@ -100,13 +100,16 @@ class CosmologicalModel(object):
         if _debug:
             self._log.debug("Starting simulation with %s.", self.solver)
         solver = getattr(rk4, self.solver)
+        extra = {}
+        if getattr(self, "row_stride", 1) != 1:      # extension: strided / last-row output
+            extra["row_stride"] = self.row_stride
         try:
             self.tresult, self.yresult = solver(ystart=self.ystart,
                                                 simtstart=self.simtstart,
                                                 tsix=self.tstartindex,
                                                 tend=self.tend,
                                                 h=self.tstep_wanted,
-                                                derivs=self.derivs)
+                                                derivs=self.derivs, **extra)
         except Exception:
             self._log.exception("Error running %s!", self.solver)
             raise
@@ -426,6 +429,8 @@ class FOCanonicalTwoStage(MultiStageDriver):
                                             k=self.k, ainit=self.ainit,
                                             potential_func=self.potential_func,
                                             pot_params=self.pot_params, nfields=self.nfields)
+        if getattr(self, "row_stride", 1) != 1:
+            self.firstordermodel.row_stride = self.row_stride
         self._log.info("Beginning first order run...")
         try:
             self.firstordermodel.run(saveresults=False)

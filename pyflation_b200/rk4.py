@@ -60,7 +60,7 @@ def _xarr(simtstart, T, h):
     return simtstart + np.arange(T) * h                     # rk4.py:78-87,134
 
 
-def rkdriver_tsix(ystart, simtstart, tsix, tend, h, derivs, yresult_out=None):
+def rkdriver_tsix(ystart, simtstart, tsix, tend, h, derivs, yresult_out=None, row_stride=1):
     """Driver function for classical Runge Kutta 4th Order method.
     Uses indexes of starting time values instead of actual times.
     Indexes are number of steps of size h away from initial time simtstart.
@@ -71,6 +71,10 @@ def rkdriver_tsix(ystart, simtstart, tsix, tend, h, derivs, yresult_out=None):
     ``yresult_out`` (extension, optional): a C-contiguous complex128 array or CPU tensor of
     shape (T, nvar, nk) to receive the first-order trajectory -- lets repeated runs reuse one
     page-locked host buffer instead of allocating tens of GB per call.
+
+    ``row_stride`` (extension, optional): keep only rows 0, s, 2s, ... of a first-order run
+    (``xarr`` is strided the same way); ``row_stride="last"`` keeps rows 0 and T-1.  Batches
+    whose full trajectory does not fit anywhere are run this way.
     """
     kind, model = _bound_model(derivs)
     tsix, T = _check_common(tsix, simtstart, tend, h)
@@ -83,11 +87,16 @@ def rkdriver_tsix(ystart, simtstart, tsix, tend, h, derivs, yresult_out=None):
         if kind == "bg":
             yarr = _run_background(model, ystart, simtstart, tsix, T, h)
         else:
-            yarr = _run_first_order(model, ystart, simtstart, tsix, T, h, yresult_out)
+            if row_stride == "last":
+                row_stride = max(1, T - 1)
+            yarr = _run_first_order(model, ystart, simtstart, tsix, T, h, yresult_out, int(row_stride))
     except _lib.ArgumentError as err:
         raise SimRunError(str(err))
     rk_log.info("Execution of Runge-Kutta method has finished.")
-    return _xarr(simtstart, T, h), yarr
+    xarr = _xarr(simtstart, T, h)
+    if kind == "fo" and row_stride != 1:
+        xarr = xarr[::int(row_stride)]
+    return xarr, yarr
 
 
 def _run_background(model, ystart, simtstart, tsix, T, h):
@@ -103,7 +112,7 @@ def _run_background(model, ystart, simtstart, tsix, T, h):
     return bg.cpu().numpy().reshape(T, 2 * nf + 1, 1)
 
 
-def _run_first_order(model, ystart, simtstart, tsix, T, h, yresult_out=None):
+def _run_first_order(model, ystart, simtstart, tsix, T, h, yresult_out=None, row_stride=1):
     import torch
     nf = model.nfields
     nvar = engine.nvar_of(nf)
@@ -119,6 +128,13 @@ def _run_first_order(model, ystart, simtstart, tsix, T, h, yresult_out=None):
     pm = engine.make_model(model.potential_func, model.pot_params, nf, model.ainit)
     prob = engine.FirstOrderProblem(pm, k, tsix, ystart.astype(np.complex128, copy=False),
                                     simtstart, T, h)
+    if row_stride < 1:
+        raise SimRunError("row_stride must be a positive integer")
+    if row_stride != 1:
+        rows = engine.first_order_device(prob, out_every=row_stride,
+                                         y0=np.real(ystart[0:2 * nf + 1, 0]), n0=n0)
+        prob.check_flags()
+        return rows.cpu().numpy()
     out = None
     if yresult_out is not None:
         out = yresult_out if torch.is_tensor(yresult_out) else torch.as_tensor(yresult_out)

@@ -299,6 +299,26 @@ def test_edge_cases_and_errors():
         mv.run(saveresults=False)
 
 
+def test_row_stride_and_last_row_output():
+    """Extension for batches whose trajectory fits nowhere: strided / last-row output through
+    the model API gives the same rows and the same final P_R as the full run."""
+    from pyflation_b200 import cosmomodels as c
+    g = load_fo("c3_hybridquadratic_2p20")
+    full = run_model(g)
+    m = getattr(c, g["cls"])(**model_kwargs(g))
+    m.row_stride = 50
+    m.run(saveresults=False)
+    assert m.yresult.shape[0] == len(m.tresult) == (g["T"] + 49) // 50
+    assert np.array_equal(m.tresult, full.tresult[::50])
+    assert np.array_equal(m.yresult.view(np.float64), np.ascontiguousarray(full.yresult[::50]).view(np.float64),
+                          equal_nan=True)
+    m = getattr(c, g["cls"])(**model_kwargs(g))
+    m.row_stride = "last"
+    m.run(saveresults=False)
+    assert m.yresult.shape[0] == 2 and m.tresult[-1] == full.tresult[-1]
+    assert rel_err(m.Pr[-1:], g["Pr_last"]) < TOL
+
+
 def test_rk4stepks_single_step():
     """rk4.rk4stepks (rk4.py:27-55) == row tsix+1 of the driver's output."""
     from pyflation_b200 import cosmomodels as c, rk4
