@@ -320,7 +320,7 @@ extern "C" int pf_fo_run(const pf_model* m, int64_t nk, const double* k_dev, con
     static const bool generic_only = getenv("PF_FO_GENERIC") != nullptr;
     switch (m->nfields) {
         case 1:
-            if (out_every == 1 && !generic_only) launch_fo1(a, st);   // full-trajectory fast path
+            if (!generic_only) launch_fo1(a, st);                     // single-field fast path
             else launch_fo<1, 2>(a, st);
             break;
         case 2: launch_fo<2, 2>(a, st); break;
@@ -362,10 +362,11 @@ extern "C" int pf_fo_solve(const pf_model* m, int64_t nk, const double* k_dev, c
     double* bg = stagey + T * (int64_t)(4 * nbg_of(nf));
     PF_CUDA_CHECK(cudaMemsetAsync(ws_dev, 0, 8 * sizeof(int32_t), st), "pf_fo_solve memset");
     static const bool no_fuse = getenv("PF_FO_NOFUSE") != nullptr;
-    if (nf == 1 && out_every == 1 && nk > 0 && t1 > 0 && !no_fuse) {
+    if (nf == 1 && nk > 0 && t1 > 0 && !no_fuse) {
         FoArgs a;
         a.nk = nk; a.k = k_dev; a.tsix = tsix_dev; a.ystart = ystart_dev; a.rec = rec;
-        a.T = T; a.t0 = 0; a.t1 = t1; a.state = state_dev; a.yout = yout_dev; a.out_every = 1;
+        a.T = T; a.t0 = 0; a.t1 = t1; a.state = state_dev;
+        a.yout = out_every > 0 ? yout_dev : nullptr; a.out_every = out_every;
         a.flags = ws_dev + 1; a.h = h; a.layout = layout;
         if (launch_fo1_fused(m, a, simtstart, n0, y0_host, rec, ws_dev, st)) {
             PF_CUDA_CHECK(cudaGetLastError(), "pf_fo_solve fused launch");

@@ -135,9 +135,12 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
     const int64_t rstride = NV * nk;
 
     // ---- regime 1: rows before any mode of this CTA starts: NaN+NaNj, no records needed
+    // rows are stored when (n - t0) is a multiple of out_every (0: never); next_out tracks it
+    const int64_t every = a.out_every;
+    int64_t next_out = (a.yout != nullptr && every > 0) ? a.t0 : INT64_MAX;
     int64_t n = a.t0;
     const int64_t nan_end = tsmin < a.t1 ? tsmin : a.t1;
-    for (; n < nan_end; ++n) {
+    for (; next_out < nan_end; next_out += every) {
 #pragma unroll
         for (int m = 0; m < KPT; ++m)
             if (live[m]) {
@@ -146,6 +149,7 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
             }
         prow += rstride;
     }
+    n = nan_end;
     if (n >= a.t1) return;
 
     // ---- regimes 2 and 3: records streamed through shared memory from row c0 on
@@ -173,11 +177,12 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
         for (int q = 0; q < cnt; ++q) {
             n = base + q;
             const Coef cf = load_record(&srec[buf][q * FO1_REC]);
+            const bool out = (n == next_out);
             if (n > tsmax) {
                 // ---- regime 3: every mode of the CTA is running
 #pragma unroll
                 for (int m = 0; m < KPT; ++m)
-                    if (live[m]) {
+                    if (live[m] && out) {
                         if constexpr (!PERT) {
                             __stcs(prow + m, make_double2(cf.bg[0], 0.0));
                             __stcs(prow + nk + m, make_double2(cf.bg[1], 0.0));
@@ -196,9 +201,11 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
                 for (int m = 0; m < KPT; ++m) {
                     if (!live[m]) continue;
                     if (n < ts[m]) {
+                        if (out) {
 #pragma unroll
-                        for (int var = 0; var < NV; ++var)
-                            __stcs(prow + var * nk + m, make_double2(nan, nan));   // rk4.py:100
+                            for (int var = 0; var < NV; ++var)
+                                __stcs(prow + var * nk + m, make_double2(nan, nan));   // rk4.py:100
+                        }
                         continue;
                     }
                     double2 b0 = make_double2(cf.bg[0], 0.0), b1 = make_double2(cf.bg[1], 0.0),
@@ -216,17 +223,22 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
                             if (bad) atomicOr(a.flags, PF_FLAG_BG_MISMATCH);
                         }
                     }
-                    if constexpr (!PERT) {
-                        __stcs(prow + m, b0);
-                        __stcs(prow + nk + m, b1);
-                        __stcs(prow + 2 * nk + m, b2);
+                    if (out) {
+                        if constexpr (!PERT) {
+                            __stcs(prow + m, b0);
+                            __stcs(prow + nk + m, b1);
+                            __stcs(prow + 2 * nk + m, b2);
+                        }
+                        __stcs(prow + XO * nk + m, make_double2(x[m][0], x[m][1]));
+                        __stcs(prow + (XO + 1) * nk + m, make_double2(v[m][0], v[m][1]));
                     }
-                    __stcs(prow + XO * nk + m, make_double2(x[m][0], x[m][1]));
-                    __stcs(prow + (XO + 1) * nk + m, make_double2(v[m][0], v[m][1]));
                     if (n + 1 < a.T) rk4_mode(cf, kval[m], h, hh, h6, x[m], v[m]);
                 }
             }
-            prow += rstride;
+            if (out) {
+                prow += rstride;
+                next_out += every;
+            }
         }
         __syncthreads();                              // everyone is done reading srec[buf]
         if (tid == 0 && c + 2 < nchunks) issue(c + 2);
@@ -390,8 +402,11 @@ static int sm_count() {
     return sms;
 }
 
-static int64_t fo1_block(int64_t nk, int sms) {
-    int max_threads = 512;
+// Full-trajectory launches are bound by the DRAM write pattern and want the largest contiguous
+// segment per CTA (512 threads = 8 KB per row); strided / state-only launches are bound by the
+// fp64 pipe and run ~10 % faster with 128-thread CTAs (measured, scripts/dev_probe.py c5).
+static int64_t fo1_block(int64_t nk, int sms, int64_t out_every) {
+    int max_threads = out_every == 1 ? 512 : 128;
     if (const char* e = getenv("PF_FO1_MAXT")) max_threads = atoi(e);
     if (max_threads < 32 || max_threads > 512) max_threads = 512;
     int64_t block = 0;
@@ -405,7 +420,7 @@ static int64_t fo1_block(int64_t nk, int sms) {
 }
 
 int launch_fo1(const FoArgs& a, cudaStream_t st) {
-    const int64_t block = fo1_block(a.nk, sm_count());
+    const int64_t block = fo1_block(a.nk, sm_count(), a.out_every);
     const int64_t grid = (a.nk + block - 1) / block;
     if (a.layout == PF_LAYOUT_PERT) fo1_kernel<true><<<(unsigned)grid, (unsigned)block, 0, st>>>(a);
     else fo1_kernel<false><<<(unsigned)grid, (unsigned)block, 0, st>>>(a);
@@ -424,7 +439,7 @@ bool launch_fo1_fused(const pf_model* m, const FoArgs& a, double simtstart, int6
     f.n0 = n0;
     f.rec = rec;
     f.ws = ws;
-    const int64_t cthreads = fo1_block(a.nk, sm_count() - 1);   // one SM hosts the producer
+    const int64_t cthreads = fo1_block(a.nk, sm_count() - 1, a.out_every);   // one SM hosts the producer
     const int64_t block = cthreads > PROD_THREADS ? cthreads : PROD_THREADS;
     const int64_t grid = (a.nk + cthreads - 1) / cthreads + 1;
 #define PF_CALL(POT, NF) \
