@@ -158,6 +158,22 @@ int pf_fo_solve(const pf_model *m, int64_t nk, const double *k_dev, const int64_
                 double simtstart, double h, int64_t t1, double *scratch_dev, double *state_dev,
                 double *yout_dev, int64_t out_every, int32_t layout, int32_t *ws_dev, void *stream);
 
+/* ---- K6 / K7: initial-condition glue on the device (FOCanonicalTwoStage.setfoics) ----
+ * pf_crossing_rows: rows_dev[k] = first row t with cum_dev[t] > k, cum_dev[T] the running
+ * maximum of cq*ainit*exp(t)*H(t) over the background rows before the end of inflation
+ * (cosmomodels.py:1074-1131); rows_dev[k] = T when there is none.  nbad_dev (may be NULL) is
+ * int32[2]: [0] += modes that never cross (ModelError at :1109), [1] += modes that cross at
+ * row 0 (ModelError at :1335).
+ * pf_bunch_davies: ystart_dev c128 [nvar][nk] from the background rows bg_dev[T][2nf+1]:
+ * background rows of the start row, diagonal mode-matrix entries in the Bunch-Davies state
+ * (cosmomodels.py:1443-1492); phase = 0 drops exp(-i k eta) (FONoPhase, :2083-2132);
+ * suppress_ix >= 0 zeroes that field's mode (FOSuppressOneField, :2144-2197), -1 = none. */
+int pf_crossing_rows(int64_t nk, const double *k_dev, int64_t T, const double *cum_dev,
+                     int64_t *rows_dev, int32_t *nbad_dev, void *stream);
+int pf_bunch_davies(int nfields, int64_t nk, const double *k_dev, const int64_t *rows_dev,
+                    const double *bg_dev, double simtstart, double h, double ainit, double etainit,
+                    int phase, int suppress_ix, double *ystart_dev, void *stream);
+
 /* ---- K5: curvature power spectrum of trajectory rows (adiabatic.py:153-285) ----
  * y_dev c128 [nrows][nvar][nk] -> Pr_dev [nrows][nk];  if k_dev != NULL the result is the
  * scaled spectrum k^3/(2 pi^2) P_R (utilities.py:12-37). */

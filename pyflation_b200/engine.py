@@ -309,3 +309,84 @@ def potential_eval_device(model, y):
         _lib.check(L.pf_potential_eval(ctypes.byref(model), n, _ptr(y), _ptr(U), _ptr(dU), _ptr(d2U),
                                        _stream_ptr()))
     return U, dU, d2U
+
+
+def device_initial_conditions(k, bg, T_infl, nf, ainit, etainit, cq, simtstart, h, phase=True,
+                              suppress_ix=None):
+    """K6 + K7: start rows and Bunch-Davies start vectors computed on the device.
+
+    ``k`` device f64 [nk]; ``bg`` device [T, 2nf+1] (background run); ``T_infl`` = fotendindex
+    (only rows before the end of inflation are searched, cosmomodels.py:1330).  Returns
+    (rows int64 [nk], ystart c128 [nvar, nk]) on the device and raises like setfoics does."""
+    from .cosmomodels import ModelError
+    L = _lib.lib()
+    dev = k.device
+    nk = k.shape[0]
+    with torch.cuda.device(dev):
+        t = simtstart + torch.arange(T_infl, dtype=torch.float64, device=dev) * h
+        aH = cq * (ainit * torch.exp(t) * bg[:T_infl, 2 * nf])
+        cum = torch.cummax(aH, dim=0).values.contiguous()
+        rows = torch.empty(nk, dtype=torch.int64, device=dev)
+        nbad = torch.zeros(2, dtype=torch.int32, device=dev)
+        _lib.check(L.pf_crossing_rows(nk, _ptr(k), int(T_infl), _ptr(cum), _ptr(rows), _ptr(nbad),
+                                      _stream_ptr()))
+        late, early = (int(v) for v in nbad.tolist())
+        if late:
+            raise ModelError("%d k modes cross the horizon after the end of inflation!" % late)
+        if early and simtstart == 0:
+            raise ModelError("Some k modes crossed horizon before simulation began and cannot "
+                             "be initialized!")
+        ystart = torch.empty((nvar_of(nf), nk), dtype=torch.complex128, device=dev)
+        _lib.check(L.pf_bunch_davies(int(nf), nk, _ptr(k), _ptr(rows), _ptr(bg.contiguous()),
+                                     float(simtstart), float(h), float(ainit), float(etainit),
+                                     1 if phase else 0, -1 if suppress_ix is None else int(suppress_ix),
+                                     _ptr(ystart), _stream_ptr()))
+    return rows, ystart
+
+
+def spectrum_run(potential_func, k, nfields=1, pot_params=None, bgystart=None, cq=50, tend=83.0,
+                 h=0.01, simtstart=0.0, phase=True, suppress_ix=None, fixed_ainit=None,
+                 row_stride="last", device=None):
+    """Device-resident two-stage run for very large k grids (BASELINE config 5: 2^20..2^24
+    modes): background run, horizon crossings, Bunch-Davies start vectors, the first-order
+    integration and P_R(k) all stay on the GPU; only scalars and the requested rows leave it.
+
+    Returns a dict: ``k``, ``fotstartindex``, ``rows`` (device c128 [R, nvar, nk], rows
+    0, s, 2s, ... of yresult), ``tresult`` of those rows, ``Pr`` / ``scaled_Pr`` (device f64
+    [R, nk]) and the scalars ``ainit, etainit, fotend, fotendindex, T``."""
+    from . import cosmomodels as c
+    dev = require_cuda(device)
+    pot_params = {} if pot_params is None else pot_params
+    nf = int(nfields)
+    m = c.FOCanonicalTwoStage(k=np.array([1e-60]), potential_func=potential_func,
+                              pot_params=pot_params, nfields=nf, bgystart=bgystart, cq=cq,
+                              tend=tend, tstep_wanted=h, simtstart=simtstart)
+    m.runbg()
+    if fixed_ainit is None:
+        ainit = float(np.ravel(m._choose_ainit())[0])
+    else:
+        ainit = float(fixed_ainit)
+    bgy = m.bgmodel.yresult[:, :, 0]
+    eps0 = 0.5 * np.sum(bgy[0, 1:2 * nf:2] ** 2)
+    etainit = float(-1 / (ainit * bgy[0, 2 * nf] * (1 - eps0)))
+    T = int(np.around((m.fotend - simtstart) / h) + 1)
+    with torch.cuda.device(dev):
+        kd = k.to(dev, torch.float64).contiguous() if torch.is_tensor(k) else \
+            torch.as_tensor(np.ascontiguousarray(k, dtype=np.float64)).to(dev)
+        bg = torch.as_tensor(np.ascontiguousarray(bgy)).to(dev)
+        rows0, ystart = device_initial_conditions(kd, bg, int(m.fotendindex), nf, ainit, etainit, cq,
+                                                  simtstart, h, phase, suppress_ix)
+        n0 = int(rows0.min().item())
+        if int(rows0[0].item()) != n0:
+            raise ValueError("k must be sorted so that column 0 starts first (cosmomodels.py:641)")
+        pm = make_model(potential_func, pot_params, nf, ainit)
+        prob = FirstOrderProblem(pm, kd, rows0, ystart, simtstart, T, h, dev)
+        stride = max(1, T - 1) if row_stride == "last" else int(row_stride)
+        y0 = bgy[n0].copy()
+        out = first_order_device(prob, out_every=stride, y0=y0, n0=n0)
+        prob.check_flags()
+        pr = pr_spectrum_device(nf, out)
+        spr = pr_spectrum_device(nf, out, kd)
+    tres = (simtstart + np.arange(T) * h)[::stride]
+    return dict(k=kd, fotstartindex=rows0, rows=out, tresult=tres, Pr=pr, scaled_Pr=spr, ainit=ainit,
+                etainit=etainit, fotend=m.fotend, fotendindex=int(m.fotendindex), T=T)

@@ -319,6 +319,37 @@ def test_row_stride_and_last_row_output():
     assert rel_err(m.Pr[-1:], g["Pr_last"]) < TOL
 
 
+@pytest.mark.parametrize("name,nk", [("c5_msqphisq_2p20", 2 ** 20), ("c3_hybridquadratic_2p20", 2 ** 20),
+                                     ("c2_lambdaphi4_2p16", 2 ** 16)])
+def test_device_resident_spectrum_run(name, nk):
+    """engine.spectrum_run: crossings (K6), Bunch-Davies vectors (K7), integration and P_R (K5)
+    all on the device, at BASELINE grid sizes; golden columns from the reference."""
+    import torch
+    from pyflation_b200 import engine
+    g = load_fo(name)
+    nf = g["nfields"]
+    k = np.linspace(KMIN, KMAX, nk)
+    res = engine.spectrum_run(g["potential"], k, nf, g["params"], g["bgystart"].copy(), cq=50)
+    cols = torch.as_tensor(g["kix"], device="cuda")
+    assert res["T"] == g["T"] and res["fotendindex"] == int(g["fotendindex"])
+    assert np.array_equal(res["fotstartindex"][cols].cpu().numpy(), g["fotstartindex"])
+    assert abs(res["ainit"] / float(g["ainit"].reshape(-1)[0]) - 1) < TOL
+    assert rel_err(res["Pr"][-1:, cols].cpu().numpy(), g["Pr_last"]) < TOL
+    assert rel_err(res["scaled_Pr"][-1:, cols].cpu().numpy(), g["scaled_Pr_last"]) < TOL
+    # start vectors: amplitudes to 1e-9 (the phase is conditioned at 1e-5, see conditioning.json)
+    y0 = res["rows"][0]                 # row 0 is NaN; compare the device start vectors instead
+    m, prob = _problem(g, k=k[g["kix"]])
+    rows, ystart = engine.device_initial_conditions(
+        torch.as_tensor(k[g["kix"]], device="cuda"), torch.as_tensor(np.ascontiguousarray(m.bgmodel.yresult[:, :, 0]), device="cuda"),
+        int(m.fotendindex), nf, float(np.ravel(m.ainit)[0]), float(np.ravel(m.etainit)[0]), 50, 0.0, 0.01)
+    ys = ystart.cpu().numpy()
+    nb = 2 * nf + 1
+    assert np.array_equal(rows.cpu().numpy(), g["fotstartindex"])
+    assert rel_err(ys[:nb], g["foystart"][:nb]) < TOL
+    assert rel_err(np.abs(ys[nb:]), np.abs(g["foystart"][nb:]), 1e-200) < TOL
+    assert rel_err(ys[nb:], g["foystart"][nb:], 1e-200) < 1e-3
+
+
 def test_rk4stepks_single_step():
     """rk4.rk4stepks (rk4.py:27-55) == row tsix+1 of the driver's output."""
     from pyflation_b200 import cosmomodels as c, rk4
