@@ -144,3 +144,25 @@ class ShardedFirstOrder(object):
         m = self.model if self.model is not None else self.prepare()
         m.runfo()
         return m
+
+
+def sharded_spectrum_run(potential_func, k, gather=True, **kwargs):
+    """BASELINE config 5: a k grid of 2^20..2^24 modes sharded over the ranks of the process
+    group.  Each rank runs the device-resident pipeline (engine.spectrum_run) on its contiguous
+    slab; the last-row spectra are assembled with one all-gather (``gather=False`` skips it).
+
+    Returns the rank's result dict plus ``bounds`` and, when gathered, ``Pr_all`` /
+    ``scaled_Pr_all`` (device f64 [R, nk]) on every rank."""
+    from . import engine
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    k = np.asarray(k, dtype=np.float64)
+    bounds = equal_slabs(len(k), world)      # state-only runs: cost ~ active steps, nearly uniform
+    res = engine.spectrum_run(potential_func, k[my_slab(bounds, rank)], **kwargs)
+    res["bounds"] = bounds
+    if gather and world > 1:
+        res["Pr_all"] = gather_spectrum(res["Pr"], bounds)
+        res["scaled_Pr_all"] = gather_spectrum(res["scaled_Pr"], bounds)
+    elif gather:
+        res["Pr_all"], res["scaled_Pr_all"] = res["Pr"], res["scaled_Pr"]
+    return res
