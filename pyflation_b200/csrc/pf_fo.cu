@@ -54,24 +54,50 @@ __device__ __forceinline__ void store_row(double* rowbase, int64_t kk, int part,
 }
 
 // kv = -(A v + (kR)^2 x + C x)        cosmomodels.py:663-674
+// Every coefficient is a broadcast shared-memory load.  With one load per DFMA the LSU (one
+// broadcast wavefront per clock per SM) would cap the fp64 pipe (two warp-DFMAs per clock per
+// SM) at ~50 %, so for even NF the 16-byte aligned rows of C are read as 128-bit pairs.
 template <int NF, int NC>
 __device__ __forceinline__ void mode_rhs(const double* __restrict__ cs, double kval,
                                          const double (&x)[NF][NC], const double (&v)[NF][NC],
                                          double (&kv)[NF][NC]) {
-    const double A = cs[0];
-    const double kr = kval * cs[1];
+    const double2 ar = *reinterpret_cast<const double2*>(cs);
+    const double A = ar.x;
+    const double kr = kval * ar.y;
     const double B = kr * kr;
+    // column-by-column accumulation: the NF row sums are independent dependency chains and are
+    // advanced together (ILP = NF*NC), instead of finishing one row's NF-long chain at a time
+    double acc[NF][NC];
 #pragma unroll
-    for (int i = 0; i < NF; ++i) {
+    for (int i = 0; i < NF; ++i)
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            double acc = A * v[i][c];
-            acc = fma(B, x[i][c], acc);
+        for (int c = 0; c < NC; ++c) acc[i][c] = fma(B, x[i][c], A * v[i][c]);
+    if constexpr (NF % 2 == 0) {
 #pragma unroll
-            for (int l = 0; l < NF; ++l) acc = fma(cs[2 + i * NF + l], x[l][c], acc);
-            kv[i][c] = -acc;
+        for (int l = 0; l < NF / 2; ++l) {
+#pragma unroll
+            for (int i = 0; i < NF; ++i) {
+                const double2 cc = reinterpret_cast<const double2*>(cs + 2 + i * NF)[l];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) acc[i][c] = fma(cc.x, x[2 * l][c], acc[i][c]);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) acc[i][c] = fma(cc.y, x[2 * l + 1][c], acc[i][c]);
+            }
         }
+    } else {
+#pragma unroll
+        for (int l = 0; l < NF; ++l)
+#pragma unroll
+            for (int i = 0; i < NF; ++i) {
+                const double cc = cs[2 + i * NF + l];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) acc[i][c] = fma(cc, x[l][c], acc[i][c]);
+            }
     }
+#pragma unroll
+    for (int i = 0; i < NF; ++i)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) kv[i][c] = -acc[i][c];
 }
 
 template <int NF, int NC>
