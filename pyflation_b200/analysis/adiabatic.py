@@ -67,6 +67,33 @@ def scaled_Pr(m, tix=None, kix=None):
     return utilities.kscaling(m.k, kix) * Pr(m, tix, kix)
 
 
+def Pzeta_spectrum(Vphi, phidot, H, modes, modesdot, axis):
+    """P_zeta = P_{delta rho} / (rho')^2 (adiabatic.py:309-352, with nonadiabatic.py:145-239,
+    433-471):  delta rho_I = sum_a [H^2 phi'_a chi'_aI - H^2 phi'_a^2/2 sum_b phi'_b chi_bI
+    + V_a chi_aI],  P_{delta rho} = sum_I |delta rho_I|^2,  rho' = -3 H^2 sum_a phi'_a^2."""
+    Vphi, phidot, H, modes, modesdot, axis = utilities.correct_shapes(Vphi, phidot, H, modes,
+                                                                      modesdot, axis)
+    pa = np.expand_dims(phidot, axis + 1)
+    Va = np.expand_dims(Vphi, axis + 1)
+    Hm = np.expand_dims(H, axis + 1)
+    inner = np.sum(pa * modes, axis=axis, keepdims=True)
+    drho = np.sum(Hm ** 2 * pa * modesdot - 0.5 * Hm ** 2 * pa ** 2 * inner + Va * modes, axis=axis)
+    spectrum = np.real(np.sum(drho * np.conj(drho), axis=axis)).astype(float)
+    rhodot = np.sum(-3 * H ** 2 * phidot ** 2, axis=axis)
+    return rhodot ** (-2.0) * spectrum
+
+
+def Pzeta(m, tix=None, kix=None):
+    """Unscaled spectrum of the curvature perturbation on uniform-density hypersurfaces
+    (adiabatic.py:287-307)."""
+    return Pzeta_spectrum(*utilities.components_from_model(m, tix, kix))
+
+
+def scaled_Pzeta(m, tix=None, kix=None):
+    """k^3/(2 pi^2) P_zeta (adiabatic.py:354-378)."""
+    return utilities.kscaling(m.k, kix) * Pzeta(m, tix, kix)
+
+
 def findns(sPr, k, kix, running=False):
     """Spectral index n_s (and running) of a scaled spectrum at ``k[kix]``
     (adiabatic.py:84-131)."""

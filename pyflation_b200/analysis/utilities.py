@@ -67,3 +67,41 @@ def makespectrum(modes_I, axis):
     """sum_I |modes_I|^2 along ``axis`` (utilities.py:255-277)."""
     modes_I = np.atleast_1d(modes_I)
     return np.real(np.sum(modes_I * modes_I.conj(), axis=axis)).astype(float)
+
+
+def correct_shapes(Vphi, phidot, H, modes, modesdot, axis):
+    """Bring the inputs of the energy-density spectra to broadcastable shapes
+    (utilities.py:279-335): Vphi and phidot (..., nfields, ...), H with a length-1 field axis,
+    modes/modesdot with two adjacent nfields-long axes starting at ``axis``."""
+    mshape = modes.shape
+    if mshape[axis + 1] != mshape[axis]:
+        raise ValueError("The mode matrix dimensions are not together.")
+    if mshape != modesdot.shape:
+        raise ValueError("Mode matrix and its derivative should be the same shape.")
+    Vphi, phidot, H = np.atleast_1d(Vphi, phidot, H)
+    if Vphi.ndim < phidot.ndim:
+        Vphi = np.expand_dims(Vphi, axis=-1)
+    if (len(mshape) - 1) != Vphi.ndim != phidot.ndim:
+        raise ValueError("Vphi, phidot and modes arrays must have correct shape.")
+    if H.ndim < phidot.ndim:
+        H = np.expand_dims(H, axis)
+    return Vphi, phidot, H, modes, modesdot, axis
+
+
+def components_from_model(m, tix=None, kix=None):
+    """(Vphi, phidot, H, modes, modesdot, axis) of model ``m`` for the requested rows and
+    modes (utilities.py:205-253); the potential gradient is evaluated with the host-side
+    ``cmpotentials`` function, row by row, as in the reference."""
+    if tix is None:
+        tslice = slice(None)
+    else:
+        if tix < 0:
+            tix = len(m.tresult) + tix
+        tslice = slice(tix, tix + 1)
+    kslice = slice(None) if kix is None else slice(kix, kix + 1)
+    phidot = m.yresult[tslice, m.phidots_ix, kslice]
+    H = m.yresult[tslice, m.H_ix, kslice]
+    Vphi = np.array([m.potentials(row, m.pot_params)[1] for row in m.yresult[tslice, m.bg_ix, kslice]])
+    modes = getmodematrix(m.yresult[tslice, m.dps_ix, kslice], m.nfields)
+    modesdot = getmodematrix(m.yresult[tslice, m.dpdots_ix, kslice], m.nfields)
+    return correct_shapes(Vphi, phidot, H, modes, modesdot, 1)

@@ -318,11 +318,13 @@ class MultiStageDriver(CosmologicalModel):
 
     @property
     def Pzeta(self):
-        raise NotImplementedError("Pzeta belongs to the non-adiabatic analysis (out of scope)")
+        """Unscaled spectrum of the curvature perturbation on uniform-density hypersurfaces."""
+        return analysis.Pzeta(self)
 
     @property
     def scaled_Pzeta(self):
-        raise NotImplementedError("scaled_Pzeta belongs to the non-adiabatic analysis (out of scope)")
+        """k^3/(2 pi^2) P_zeta for all rows and k."""
+        return analysis.scaled_Pzeta(self)
 
     def getfoystart(self):
         pass

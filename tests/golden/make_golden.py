@@ -241,14 +241,49 @@ def make_kat(ref):
     print("kat_adiabatic -> %.0f KB" % (os.path.getsize(path) / 1024.0))
 
 
+def make_pzeta(ref):
+    """P_zeta of the last stored rows of every first-order golden file, computed by the
+    reference's analysis.Pzeta on a model with injected yresult (the way the reference's own
+    tests build their models, test_adiabatic.py:138-144), plus the reference's hand-computed
+    Pzeta_spectrum vectors (test_adiabatic.py:262-327)."""
+    import glob
+    out = {}
+    for path in sorted(glob.glob(os.path.join(HERE, "fo_*.npz"))):
+        name = os.path.basename(path)[3:-4]
+        g = np.load(path)
+        nf = int(g["nfields"])
+        params = {str(a): (int(b) if str(a) == "nfields" else float(b)) for a, b in zip(g["param_keys"], g["param_vals"])}
+        m = ref.cosmomodels.FOCanonicalTwoStage(k=g["k"], nfields=nf, potential_func=str(g["potential"]),
+                                                pot_params=params)
+        m.yresult = g["yrows"][-3:]
+        m.tresult = g["tresult"][g["rows"][-3:]]
+        out[name + "_Pzeta"] = ref.analysis.Pzeta(m)
+        out[name + "_scaled_Pzeta"] = ref.analysis.scaled_Pzeta(m, tix=-1)
+    ad = ref.analysis.adiabatic
+    out["kat_single"] = np.asarray(ad.Pzeta_spectrum(3, 0.5, 2, np.array([[7]]), np.array([[5]]), 0))
+    out["kat_two"] = ad.Pzeta_spectrum(np.array([5.5, 2.3]).reshape((2, 1)), np.array([2, 5]).reshape((2, 1)),
+                                       np.array([3]).reshape((1, 1)),
+                                       np.array([[1 / 3.0, 0.1], [0.1, 0.5]]).reshape((2, 2, 1)),
+                                       np.array([[0.1, 0.2], [0.2, 1 / 7.0]]).reshape((2, 2, 1)), 0)
+    out["kat_complex"] = ad.Pzeta_spectrum(np.array([1, 2]).reshape((2, 1)), np.array([1, 1]).reshape((2, 1)),
+                                           np.array([1]).reshape((1, 1)),
+                                           np.array([[1, 1j], [-1j, 3 - 1j]]).reshape((2, 2, 1)),
+                                           np.array([[1, -1j], [1j, 3 + 1j]]).reshape((2, 2, 1)), 0)
+    path = os.path.join(HERE, "pzeta.npz")
+    np.savez_compressed(path, **out)
+    print("pzeta -> %.0f KB" % (os.path.getsize(path) / 1024.0))
+
+
 def main(argv):
     ref = ref_shim.load()
-    names = argv[1:] or (["potentials", "kat"] + list(FIXTURES))
+    names = argv[1:] or (["potentials", "kat"] + list(FIXTURES) + ["pzeta"])
     for name in names:
         if name == "potentials":
             make_potentials(ref)
         elif name == "kat":
             make_kat(ref)
+        elif name == "pzeta":
+            make_pzeta(ref)
         else:
             make_fo(ref, name)
 

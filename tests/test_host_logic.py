@@ -130,6 +130,37 @@ def test_analysis_known_answers():
         utilities.getmodematrix(np.zeros((2, 5, 3)), 2)
 
 
+def test_pzeta_against_reference():
+    """analysis.Pzeta / Pzeta_spectrum: the reference's hand-computed vectors
+    (test_adiabatic.py:262-327) and its Pzeta of the last rows of every golden run."""
+    from pyflation_b200 import cosmomodels as c
+    from pyflation_b200.analysis import adiabatic
+    from conftest import fo_fixture_names
+    g = np.load(os.path.join(GOLDEN, "pzeta.npz"))
+    arr = adiabatic.Pzeta_spectrum(3, 0.5, 2, np.array([[7]]), np.array([[5]]), 0)
+    np.testing.assert_almost_equal(arr, 29.25 ** 2 / 9.0)
+    two = adiabatic.Pzeta_spectrum(np.array([5.5, 2.3]).reshape((2, 1)), np.array([2, 5]).reshape((2, 1)),
+                                   np.array([3]).reshape((1, 1)),
+                                   np.array([[1 / 3.0, 0.1], [0.1, 0.5]]).reshape((2, 2, 1)),
+                                   np.array([[0.1, 0.2], [0.2, 1 / 7.0]]).reshape((2, 2, 1)), 0)
+    np.testing.assert_almost_equal(two, [135451.600445493 / 783 ** 2])
+    np.testing.assert_allclose(two, g["kat_two"], rtol=1e-14)
+    cx = adiabatic.Pzeta_spectrum(np.array([1, 2]).reshape((2, 1)), np.array([1, 1]).reshape((2, 1)),
+                                  np.array([1]).reshape((1, 1)),
+                                  np.array([[1, 1j], [-1j, 3 - 1j]]).reshape((2, 2, 1)),
+                                  np.array([[1, -1j], [1j, 3 + 1j]]).reshape((2, 2, 1)), 0)
+    np.testing.assert_almost_equal(cx, [38 / 36.0])
+    assert not np.iscomplexobj(cx)
+    for name in fo_fixture_names():
+        f = load_fo(name)
+        m = c.FOCanonicalTwoStage(k=f["k"], nfields=f["nfields"], potential_func=f["potential"],
+                                  pot_params=dict(f["params"]))
+        m.yresult = f["yrows"][-3:]
+        m.tresult = f["tresult"][f["rows"][-3:]]
+        assert rel_err(m.Pzeta, g[name + "_Pzeta"]) < 1e-12, name
+        assert rel_err(m.scaled_Pzeta[-1:], g[name + "_scaled_Pzeta"]) < 1e-12, name
+
+
 def test_helpers_default_grid():
     from pyflation_b200 import helpers
     kend = helpers.getkend(0.85e-60, 0.4e-60, 1025)
