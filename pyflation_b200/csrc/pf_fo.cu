@@ -100,8 +100,13 @@ __device__ __forceinline__ void mode_rhs(const double* __restrict__ cs, double k
         for (int c = 0; c < NC; ++c) kv[i][c] = -acc[i][c];
 }
 
+// nf >= 5: cap the registers at 168 so three 128-thread CTAs fit an SM (12 warps instead of 8;
+// measured +3 % at nf = 8; a cap of 128 registers spills and is slower)
+#ifndef PF_FO_MINB
+#define PF_FO_MINB(NF) ((NF) >= 5 ? 3 : 1)
+#endif
 template <int NF, int NC>
-__global__ void __launch_bounds__(FoShape<NF>::BLOCK) fo_rk4_kernel(FoArgs a) {
+__global__ void __launch_bounds__(FoShape<NF>::BLOCK, PF_FO_MINB(NF)) fo_rk4_kernel(FoArgs a) {
     using S = FoShape<NF>;
     constexpr int NB = S::NB, SW = S::SW, REC = S::REC, CH = S::CH;
     const bool pert = a.layout == PF_LAYOUT_PERT;     // perturbation rows only
