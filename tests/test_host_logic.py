@@ -188,3 +188,18 @@ def test_no_cpu_fallback():
     with pytest.raises(rk4.SimRunError):
         rk4.rkdriver_tsix(np.ones((3, 1)), 0.0, np.array([500]), 1.0, 0.01,
                           c.CanonicalBackground(ystart=np.array([18.0, -0.1, 1e-5])).derivs)
+
+
+def test_bench_reference_arm_on_cpu():
+    """bench.py's CPU arm (the oracle port, one process per shard) on a tiny sample: the
+    reference leg of the benchmark must run without a GPU."""
+    import bench
+    arm = bench.CpuArm(nk_worker=16, cores=2)
+    try:
+        wall, work = arm.step()
+    finally:
+        arm.close()
+    assert wall > 0 and work > 2 * 16 * 5000       # ~6000 active steps per mode
+    assert "2 processes x 16 consecutive modes" in arm.sample
+    cfg = bench.workload_config(1)
+    assert cfg["nk_per_gpu"] == 2 ** 16 and cfg["potential"] == "lambdaphi4"
