@@ -263,7 +263,9 @@ def first_order_host(prob, out=None, slab_bytes=1 << 30, ring=None, y0=None, n0=
                 # time step while the remaining windows compute and copy
                 rec_host = prob.rec.cpu().numpy()
                 bg_off = 4 * (2 + nf * nf)
-                nthreads = fill_threads or len(os.sched_getaffinity(0))
+                # share the host cores between the ranks of one box (torchrun sets LOCAL_WORLD_SIZE)
+                local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+                nthreads = fill_threads or max(1, len(os.sched_getaffinity(0)) // local_world)
 
                 def _fill():
                     fill_rc.append(L.pf_host_fill_background(
