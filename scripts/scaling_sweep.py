@@ -27,7 +27,14 @@ def main():
                 dist.barrier()
             torch.cuda.synchronize(); t0 = time.perf_counter()
             res = parallel.sharded_spectrum_run("msqphisq", k, nfields=1, pot_params={"nfields": 1},
-                                                bgystart=np.array([18.0, -0.1, 0.0]), cq=50)
+                                                bgystart=np.array([18.0, -0.1, 0.0]), cq=50, gather=False)
+            torch.cuda.synchronize()
+            t_local = time.perf_counter() - t0
+            if world > 1:
+                res["Pr_all"] = parallel.gather_spectrum(res["Pr"], res["bounds"])
+                res["scaled_Pr_all"] = parallel.gather_spectrum(res["scaled_Pr"], res["bounds"])
+            else:
+                res["Pr_all"], res["scaled_Pr_all"] = res["Pr"], res["scaled_Pr"]
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
@@ -38,7 +45,7 @@ def main():
             dist.all_reduce(tot)
         pr = res["Pr_all"][-1]
         if rank == 0:
-            print(json.dumps({"nk": nk, "n_gpus": world, "wall_s": wall, "mode_steps": float(tot[0]),
+            print(json.dumps({"nk": nk, "n_gpus": world, "wall_s": wall, "rank0_local_s": t_local, "mode_steps": float(tot[0]),
                               "pipeline_mode_steps_per_s": float(tot[0]) / wall,
                               "scaled_Pr_first_last": [float(res["scaled_Pr_all"][-1, 0]), float(res["scaled_Pr_all"][-1, -1])],
                               "finite": bool(torch.isfinite(pr).all())}))
