@@ -416,3 +416,24 @@ def test_pr_kernel_known_answers():
     k = torch.as_tensor(np.array([1e-60, 5.25e-60]), device="cuda")
     np.testing.assert_allclose(engine.pr_spectrum_device(3, y, k).cpu().numpy(),
                                g["block_Pr"] * (k.cpu().numpy() ** 3 / (2 * np.pi ** 2)), rtol=1e-13)
+
+
+def test_firstorder_script(tmp_path):
+    """bin/pyflation_firstorder.py (the caller of the hot path, reference bin/pyflation_firstorder.py):
+    default msqphisq fixture on every 64th k of the K4 range == BASELINE config 1's golden columns."""
+    import subprocess, sys
+    from conftest import ROOT
+    g = load_fo("c1_msqphisq_k4")
+    out = str(tmp_path / "fo.npz")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "pyflation_firstorder.py"), "-f", out,
+                          "-p", "msqphisq", "--kstride", "64", "--console", "-v"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    z = np.load(out)
+    assert z["yresult"].shape == (g["T"], 5, 33)
+    pick = cols = [0, 1, 2, 3, 4]                      # k indices 0, 64, ..., 256 are in both sub-grids
+    assert np.array_equal(z["k"][pick], g["k"][cols])
+    assert mode_rel_err(z["yresult"][g["rows"]][:, :, pick], g["yrows"][:, :, cols], 1) < TOL
+    # a second run onto the same file is refused, as in the reference (:192-193)
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "pyflation_firstorder.py"), "-f", out],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode != 0 and "already exists" in res.stderr
