@@ -105,6 +105,13 @@ double pf_potential_param_default(int id, int i);
 int pf_potential_eval(const pf_model *m, int64_t n, const double *y_dev, double *U_dev,
                       double *dU_dev, double *d2U_dev, void *stream);
 
+/* ---- K8: one right-hand-side evaluation (API completeness; not used by the solvers) ----
+ * dydx = derivs(y, t) for y c128 [rows][ncol]: first_order = 1 -> CanonicalFirstOrder.derivs
+ * (cosmomodels.py:625-675, rows = nvar, k_dev[ncol] required); first_order = 0 ->
+ * CanonicalBackground.derivs (:551-571, rows = 2nf+1).  The potential is evaluated on column 0. */
+int pf_derivs(const pf_model *m, int first_order, int64_t ncol, const double *y_dev, double t,
+              const double *k_dev, double *dydx_dev, void *stream);
+
 /* ---- sizes ---- */
 int64_t pf_number_of_steps(double simtstart, double tend, double h);  /* rk4.py:73 */
 int64_t pf_nvar(int nfields);                      /* 2 nf^2 + 2 nf + 1 */

@@ -22,7 +22,7 @@ EXPORTS = [
     "pf_potential_param_default", "pf_potential_eval", "pf_number_of_steps", "pf_nvar",
     "pf_rec_doubles", "pf_bg_run", "pf_stage_table", "pf_fo_run", "pf_solve_scratch_doubles",
     "pf_fo_solve", "pf_pr_spectrum", "pf_scatter_slab", "pf_copy_rows_d2h",
-    "pf_host_fill_background", "pf_crossing_rows", "pf_bunch_davies",
+    "pf_host_fill_background", "pf_crossing_rows", "pf_bunch_davies", "pf_derivs",
 ]
 
 
@@ -96,6 +96,7 @@ def lib():
     L.pf_crossing_rows.argtypes = [c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]
     L.pf_bunch_davies.argtypes = [c_int, c_i64, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_dbl, c_dbl, c_int,
                                   c_int, c_vp, c_vp]
+    L.pf_derivs.argtypes = [mp, c_int, c_i64, c_vp, c_dbl, c_vp, c_vp, c_vp]
     _lib = L
     return L
 

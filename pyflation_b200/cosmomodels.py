@@ -184,12 +184,6 @@ class PhiModels(CosmologicalModel):
         return endefold, endindex
 
 
-def _device_only(name):
-    raise NotImplementedError(
-        "%s is evaluated inside the CUDA kernels (csrc/pf_bg.cu, csrc/pf_fo.cu); it is not "
-        "callable from Python and there is no CPU implementation in this package" % name)
-
-
 class CanonicalBackground(PhiModels):
     """Background model in e-fold time: y = (phi_i, dphi_i/dn, ..., H).
     (cosmomodels.py:525-571)"""
@@ -205,8 +199,12 @@ class CanonicalBackground(PhiModels):
             self.ystart[self.H_ix] = self.findH(U, self.ystart)
 
     def derivs(self, y, t, **kwargs):
-        """Background equations of motion -- device code (pf_bg.cu: bg_rhs)."""
-        _device_only("CanonicalBackground.derivs")
+        """Basic background equations of motion, dydx[0] = dy[0]/dn etc.  Evaluated on the GPU
+        (pf_derivs); the solver never calls this method, it recognises it and runs the fused
+        background kernel instead."""
+        from . import engine
+        pm = engine.make_model(self.potential_func, self.pot_params, self.nfields)
+        return engine.derivs_device(pm, y, t)
 
 
 class CanonicalFirstOrder(PhiModels):
@@ -235,8 +233,15 @@ class CanonicalFirstOrder(PhiModels):
         self.dpdots_ix = slice(nf * 2 + 2, None, 2)
 
     def derivs(self, y, t, **kwargs):
-        """First order equations of motion -- device code (pf_fo.cu: mode_rhs)."""
-        _device_only("CanonicalFirstOrder.derivs")
+        """Return derivatives of fields in y at time t (cosmomodels.py:625-675).  Evaluated on
+        the GPU (pf_derivs); the solver never calls this method, it recognises it and runs the
+        fused first-order kernels instead."""
+        from . import engine
+        k = kwargs.get("k")
+        if k is None:
+            k = self.k
+        pm = engine.make_model(self.potential_func, self.pot_params, self.nfields, self.ainit)
+        return engine.derivs_device(pm, y, t, k)
 
 
 class MultiStageDriver(CosmologicalModel):

@@ -153,6 +153,72 @@ __global__ void potential_eval_kernel(PotParams par, int64_t n, const double* __
     }
 }
 
+// K8: one evaluation of the right-hand side, dydx = derivs(y, t), for API completeness
+// (CanonicalFirstOrder.derivs cosmomodels.py:625-675, CanonicalBackground.derivs :551-571).
+// Complex arithmetic throughout, each column with its own background rows, the potential
+// evaluated on the (real part of the) background of column 0 -- the reference's semantics.
+struct cplx { double re, im; };
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return {a.re + b.re, a.im + b.im}; }
+__device__ __forceinline__ cplx cscale(double s, cplx a) { return {s * a.re, s * a.im}; }
+__device__ __forceinline__ cplx cinv(cplx a) {
+    const double d = a.re * a.re + a.im * a.im;
+    return {a.re / d, -a.im / d};
+}
+
+template <int POT, int NF>
+__global__ void derivs_kernel(PotParams par, double ainit, int first_order, int64_t ncol, double t,
+                              const cplx* __restrict__ y, const double* __restrict__ k,
+                              cplx* __restrict__ dydx) {
+    constexpr int NB = 2 * NF + 1;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncol) return;
+    double phi0[NF], dU[NF], d2U[NF * NF], U;
+#pragma unroll
+    for (int i = 0; i < NF; ++i) phi0[i] = y[(int64_t)(2 * i) * ncol].re;       // column 0
+    potential<POT, NF, true>(par.v, phi0, U, dU, d2U);
+    cplx pd[NF];
+#pragma unroll
+    for (int i = 0; i < NF; ++i) pd[i] = y[(int64_t)(2 * i + 1) * ncol + c];
+    const cplx H = y[(int64_t)(2 * NF) * ncol + c];
+    const cplx invH2 = cinv(cmul(H, H));
+    cplx s = {0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+        dydx[(int64_t)(2 * i) * ncol + c] = pd[i];
+        cplx num = cscale(U, pd[i]);
+        num.re += dU[i];
+        const cplx q = cmul(num, invH2);
+        dydx[(int64_t)(2 * i + 1) * ncol + c] = {-q.re, -q.im};
+        s = cadd(s, cmul(pd[i], pd[i]));
+    }
+    const cplx dH = cmul(cscale(-0.5, s), H);
+    dydx[(int64_t)(2 * NF) * ncol + c] = dH;
+    if (!first_order) return;
+    const cplx aH = cscale(ainit * exp(t), H);
+    const cplx kr = cscale(k[c], cinv(aH));
+    const cplx kr2 = cmul(kr, kr);
+#pragma unroll
+    for (int i = 0; i < NF; ++i)
+#pragma unroll
+        for (int j = 0; j < NF; ++j) {
+            const int64_t row = NB + 2 * (i * NF + j);
+            const cplx dp = y[row * ncol + c], dpd = y[(row + 1) * ncol + c];
+            cplx inner = {0.0, 0.0};
+#pragma unroll
+            for (int l = 0; l < NF; ++l) {
+                cplx M = cadd(cscale(dU[l], pd[i]), cscale(dU[i], pd[l]));
+                M = cadd(M, cscale(U, cmul(pd[i], pd[l])));
+                M.re += d2U[i * NF + l];
+                inner = cadd(inner, cmul(M, y[(int64_t)(NB + 2 * (l * NF + j)) * ncol + c]));
+            }
+            cplx tot = cadd(cmul(cscale(U, dpd), invH2), cmul(kr2, dp));
+            tot = cadd(tot, cmul(inner, invH2));
+            dydx[row * ncol + c] = dpd;
+            dydx[(row + 1) * ncol + c] = {-tot.re, -tot.im};
+        }
+}
+
 static PotParams pack_params(const pf_model* m) {
     PotParams p;
     for (int i = 0; i < PF_MAX_PARAMS; ++i) p.v[i] = m->params[i];
@@ -220,5 +286,25 @@ extern "C" int pf_potential_eval(const pf_model* m, int64_t n, const double* y_d
 #undef PF_CALL
     if (!ok) { set_error("pf_potential_eval: potential %d is not defined for nfields=%d", m->potential_id, m->nfields); return PF_E_POTENTIAL; }
     PF_CUDA_CHECK(cudaGetLastError(), "pf_potential_eval launch");
+    return PF_OK;
+}
+
+extern "C" int pf_derivs(const pf_model* m, int first_order, int64_t ncol, const double* y_dev, double t,
+                         const double* k_dev, double* dydx_dev, void* stream) {
+    int rc = check_model(m);
+    if (rc) return rc;
+    if (ncol < 0) { set_error("pf_derivs: negative size"); return PF_E_ARG; }
+    if (ncol == 0) return PF_OK;
+    if (!y_dev || !dydx_dev || (first_order && !k_dev)) { set_error("pf_derivs: null buffer"); return PF_E_ARG; }
+    PotParams par = pack_params(m);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int block = 64;
+    const int64_t grid = (ncol + block - 1) / block;
+#define PF_CALL(POT, NF) \
+    derivs_kernel<POT, NF><<<(unsigned)grid, block, 0, st>>>(par, m->ainit, first_order, ncol, t, (const cplx*)y_dev, k_dev, (cplx*)dydx_dev)
+    bool ok = PF_DISPATCH_POT_NF(m->potential_id, m->nfields, PF_CALL);
+#undef PF_CALL
+    if (!ok) { set_error("pf_derivs: potential %d is not defined for nfields=%d", m->potential_id, m->nfields); return PF_E_POTENTIAL; }
+    PF_CUDA_CHECK(cudaGetLastError(), "pf_derivs launch");
     return PF_OK;
 }

@@ -392,3 +392,31 @@ def spectrum_run(potential_func, k, nfields=1, pot_params=None, bgystart=None, c
     tres = (simtstart + np.arange(T) * h)[::stride]
     return dict(k=kd, fotstartindex=rows0, rows=out, tresult=tres, Pr=pr, scaled_Pr=spr, ainit=ainit,
                 etainit=etainit, fotend=m.fotend, fotendindex=int(m.fotendindex), T=T)
+
+
+def derivs_device(model, y, t, k=None):
+    """K8: dydx = derivs(y, t) on the device.  ``y`` array-like [rows] or [rows, ncol]; first
+    order when ``k`` is given (rows = nvar), background otherwise (rows = 2nf+1).  Returns a
+    NumPy array shaped and typed like ``y``."""
+    L = _lib.lib()
+    dev = require_cuda()
+    ynp = np.asarray(y)
+    single = ynp.ndim == 1
+    y2 = ynp[:, None] if single else ynp
+    rows, ncol = y2.shape
+    nf = model.nfields
+    want = nvar_of(nf) if k is not None else 2 * nf + 1
+    if rows != want:
+        raise ValueError("y must have %d rows" % want)
+    with torch.cuda.device(dev):
+        yd = torch.as_tensor(np.ascontiguousarray(y2, dtype=np.complex128)).to(dev)
+        kd = None if k is None else torch.as_tensor(np.ascontiguousarray(np.atleast_1d(k), dtype=np.float64)).to(dev)
+        if kd is not None and kd.shape[0] != ncol:
+            raise ValueError("k must have one entry per column of y")
+        out = torch.empty_like(yd)
+        _lib.check(L.pf_derivs(ctypes.byref(model), 1 if k is not None else 0, ncol, _ptr(yd), float(t),
+                               _ptr(kd), _ptr(out), _stream_ptr()))
+        res = out.cpu().numpy()
+    if not np.iscomplexobj(ynp):
+        res = np.ascontiguousarray(res.real)
+    return res[:, 0] if single else res

@@ -437,3 +437,32 @@ def test_firstorder_script(tmp_path):
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "pyflation_firstorder.py"), "-f", out],
                          capture_output=True, text=True, timeout=300)
     assert res.returncode != 0 and "already exists" in res.stderr
+
+
+@pytest.mark.parametrize("pot,nf,params", [("msqphisq", 1, {}), ("step_potential", 1, {}),
+                                           ("hybridquartic", 2, {}), ("nflation", 3, {"nfields": 3}),
+                                           ("nflation", 8, {"nfields": 8})])
+def test_derivs_method_matches_oracle(oracle, pot, nf, params):
+    """model.derivs(y, t) (K8) against the oracle's restatement of CanonicalFirstOrder.derivs /
+    CanonicalBackground.derivs at random complex states."""
+    from pyflation_b200 import cosmomodels as c
+    rng = np.random.RandomState(11)
+    nk, nvar, nb = 37, 2 * nf * nf + 2 * nf + 1, 2 * nf + 1
+    k = np.sort(rng.uniform(1e-60, 1e-58, nk))
+    y = rng.standard_normal((nvar, nk)) + 1j * rng.standard_normal((nvar, nk))
+    y[:nb] = 0
+    y[0:2 * nf:2] = rng.uniform(0.05, 15.0, (nf, 1)) * (1 + 1e-3 * rng.standard_normal((nf, nk)))
+    y[1:2 * nf:2] = rng.uniform(-0.2, 0.2, (nf, nk))
+    y[2 * nf] = rng.uniform(1e-6, 5e-5, nk)
+    y[nb:] *= 1e85
+    ainit, t = 7.8e-65, 31.7
+    fo = c.CanonicalFirstOrder(k=k, ainit=ainit, ystart=y.copy(), potential_func=pot, pot_params=params, nfields=nf)
+    got = fo.derivs(y, t)
+    want = oracle.make_fo_rhs(pot, params, nf, k, ainit)(y, t)
+    assert got.shape == want.shape and got.dtype == np.complex128
+    assert rel_err(got[:nb], want[:nb], 1e-300) < 1e-12
+    assert mode_rel_err(got[None], want[None], nf) < 1e-12
+    bg = c.CanonicalBackground(ystart=np.real(y[:nb, 0]).copy(), potential_func=pot, pot_params=params, nfields=nf)
+    yb = np.real(y[:nb, :1]).copy()
+    np.testing.assert_allclose(bg.derivs(yb, t), oracle.make_bg_rhs(pot, params, nf)(yb, t), rtol=1e-12)
+    assert bg.derivs(yb[:, 0], t).shape == (nb,)

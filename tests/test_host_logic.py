@@ -180,7 +180,7 @@ def test_no_cpu_fallback():
         m.run(saveresults=False)
     with pytest.raises(NotImplementedError):
         rk4.rkdriver_tsix(np.ones(2), 0.0, np.array([0]), 1.0, 0.01, lambda y, t: -y)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(_lib.LibraryError):
         c.CanonicalFirstOrder(k=np.array([1.0]), ystart=np.ones(5)).derivs(np.ones((5, 1)), 0.0)
     with pytest.raises(rk4.SimRunError):
         rk4.rkdriver_tsix(np.ones((3, 1)), 0.0, np.array([0]), 1.0, None,
