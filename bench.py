@@ -403,6 +403,13 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only")
     ap.add_argument("--cpu-warmup", action="store_true")
     args = ap.parse_args()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ and args.impl == "ours":
+        # asked for N GPUs outside torchrun: launch one rank per GPU ourselves
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29540"),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -19,6 +19,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_sessionstart(session):
+    """The C-ABI library is built in-tree; build it when a fresh checkout runs the tests."""
+    lib = os.path.join(ROOT, "pyflation_b200", "lib", "libpyflation_b200.so")
+    if not os.path.exists(lib):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
 def fo_fixture_names():
     return sorted(os.path.basename(p)[3:-4] for p in glob.glob(os.path.join(GOLDEN, "fo_*.npz")))
 
