@@ -8,30 +8,11 @@
 #include "pf_common.cuh"
 #include "pf_fo_shared.cuh"
 #include "pf_potentials.cuh"
+#include "pf_records.cuh"
 
 namespace pf {
 
 struct BgState { double v[2 * PF_MAX_NFIELDS + 1]; };
-
-template <int POT, int NF>
-__device__ __forceinline__ void bg_rhs(const double* __restrict__ p, const double (&y)[2 * NF + 1],
-                                       double (&dy)[2 * NF + 1]) {
-    double phi[NF], dU[NF], d2U[NF * NF], U;
-#pragma unroll
-    for (int i = 0; i < NF; ++i) phi[i] = y[2 * i];
-    potential<POT, NF, false>(p, phi, U, dU, d2U);
-    const double H = y[2 * NF];
-    const double invH2 = 1.0 / (H * H);
-    double s = 0.0;
-#pragma unroll
-    for (int i = 0; i < NF; ++i) {
-        const double pd = y[2 * i + 1];
-        dy[2 * i] = pd;                                   // cosmomodels.py:563
-        dy[2 * i + 1] = -(U * pd + dU[i]) * invH2;        // :566
-        s += pd * pd;
-    }
-    dy[2 * NF] = -0.5 * s * H;                            // :569
-}
 
 // One thread integrates; the rest of the warp NaN-fills rows before n0 and leaves.
 template <int POT, int NF>
@@ -108,29 +89,7 @@ __global__ void stage_table_kernel(PotParams par, double ainit, int64_t T, doubl
     double y[NB];
 #pragma unroll
     for (int c = 0; c < NB; ++c) y[c] = stagey[(n * 4 + s) * NB + c];
-    const double x = simtstart + (double)n * h;           // rk4.py:118 last_x
-    const double t = (s == 0) ? x : ((s == 3) ? x + h : x + h * 0.5);
-    const double a = ainit * exp(t);                      // cosmomodels.py:637
-    double phi[NF], pd[NF], dU[NF], d2U[NF * NF], U;
-#pragma unroll
-    for (int i = 0; i < NF; ++i) { phi[i] = y[2 * i]; pd[i] = y[2 * i + 1]; }
-    potential<POT, NF, true>(par.v, phi, U, dU, d2U);
-    const double H = y[2 * NF];
-    const double invH2 = 1.0 / (H * H);
-    double* o = r + s * SW;
-    o[0] = U * invH2;                                     // A  (:673  U*y'/H**2)
-    o[1] = 1.0 / (a * H);                                 // R  (:673  k/(a*H))
-#pragma unroll
-    for (int i = 0; i < NF; ++i)
-#pragma unroll
-        for (int l = 0; l < NF; ++l)                      // :667-669 and /H**2 at :674
-            o[2 + i * NF + l] =
-                (d2U[i * NF + l] + pd[i] * dU[l] + dU[i] * pd[l] + pd[i] * pd[l] * U) * invH2;
-    if (s == 0) {
-#pragma unroll
-        for (int c = 0; c < NB; ++c) r[BG + c] = y[c];
-    }
-    if (s == 3 && (NB + 4 * SW) < REC) r[REC - 1] = 0.0;
+    stage_record<POT, NF>(par.v, ainit, simtstart, h, n, s, y, r);
 }
 
 template <int POT, int NF>

@@ -67,20 +67,6 @@ __device__ __forceinline__ void rk4_mode(const Coef& c, double kval, double h, d
     }
 }
 
-// Fused launches: records are produced by another CTA of the same grid; wait (acquire) until
-// `need` of them are published, then order the generic-proxy writes before the TMA read.
-__device__ __forceinline__ void wait_progress(const long long* progress, long long need) {
-    long long have;
-    unsigned spins = 0;
-    for (;;) {
-        asm volatile("ld.acquire.gpu.global.s64 %0, [%1];" : "=l"(have) : "l"(progress) : "memory");
-        if (have >= need) break;
-        __nanosleep(128);
-        if (++spins > (1u << 27)) __trap();           // ~20 s: the producer died; fail, do not hang
-    }
-    asm volatile("fence.proxy.async;" ::: "memory");
-}
-
 // Consumer: integrates the modes of logical CTA `cta` (nthreads threads, KPT modes each).
 // `progress` (may be null) is the producer's published record count in fused launches.
 template <int KPT, bool PERT>

@@ -1,0 +1,306 @@
+// Generic first-order consumer (any nf, any output stride): shared by the plain kernel
+// (pf_fo.cu) and the fused producer/consumer launch (pf_fused.cu).  See pf_fo.cu for the design.
+#pragma once
+#include "pf_common.cuh"
+#include "pf_fo_shared.cuh"
+
+namespace pf {
+
+template <int NF>
+struct FoShape {
+    static constexpr int NB = 2 * NF + 1;
+    static constexpr int SW = 2 + NF * NF;          // doubles per stage: A, R, C[NF][NF]
+    static constexpr int REC = rec_of(NF);
+    static constexpr int BG_OFF = 4 * SW;           // background row sits after the 4 stages
+    static constexpr int CH_RAW = 16384 / (REC * 8);
+    static constexpr int CH = CH_RAW > 64 ? 64 : (CH_RAW < 8 ? 8 : CH_RAW);  // steps per chunk
+#ifndef PF_FO_BLOCK
+#define PF_FO_BLOCK 128
+#endif
+    static constexpr int BLOCK = PF_FO_BLOCK;
+};
+
+template <class T>
+__device__ __forceinline__ void plain_store(T* p, T v) { *p = v; }
+
+// one complex (NC = 2) or one real component (NC = 1) per row, per thread
+template <int NC>
+__device__ __forceinline__ void store_row(double* rowbase, int64_t kk, int part, const double (&c)[NC]) {
+#ifndef PF_STORE
+#define PF_STORE __stcs
+#endif
+    if constexpr (NC == 2) {
+        PF_STORE(reinterpret_cast<double2*>(rowbase) + kk, make_double2(c[0], c[1]));
+    } else {
+        PF_STORE(rowbase + 2 * kk + part, c[0]);
+    }
+}
+
+// kv = -(A v + (kR)^2 x + C x)        cosmomodels.py:663-674
+// Every coefficient is a broadcast shared-memory load.  With one load per DFMA the LSU (one
+// broadcast wavefront per clock per SM) would cap the fp64 pipe (two warp-DFMAs per clock per
+// SM) at ~50 %, so for even NF the 16-byte aligned rows of C are read as 128-bit pairs.
+template <int NF, int NC>
+__device__ __forceinline__ void mode_rhs(const double* __restrict__ cs, double kval,
+                                         const double (&x)[NF][NC], const double (&v)[NF][NC],
+                                         double (&kv)[NF][NC]) {
+    const double2 ar = *reinterpret_cast<const double2*>(cs);
+    const double A = ar.x;
+    const double kr = kval * ar.y;
+    const double B = kr * kr;
+    // column-by-column accumulation: the NF row sums are independent dependency chains and are
+    // advanced together (ILP = NF*NC), instead of finishing one row's NF-long chain at a time
+    double acc[NF][NC];
+#pragma unroll
+    for (int i = 0; i < NF; ++i)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[i][c] = fma(B, x[i][c], A * v[i][c]);
+    if constexpr (NF % 2 == 0) {
+#pragma unroll
+        for (int l = 0; l < NF / 2; ++l) {
+#pragma unroll
+            for (int i = 0; i < NF; ++i) {
+                const double2 cc = reinterpret_cast<const double2*>(cs + 2 + i * NF)[l];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) acc[i][c] = fma(cc.x, x[2 * l][c], acc[i][c]);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) acc[i][c] = fma(cc.y, x[2 * l + 1][c], acc[i][c]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int l = 0; l < NF; ++l)
+#pragma unroll
+            for (int i = 0; i < NF; ++i) {
+                const double cc = cs[2 + i * NF + l];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) acc[i][c] = fma(cc, x[l][c], acc[i][c]);
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < NF; ++i)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) kv[i][c] = -acc[i][c];
+}
+
+// nf >= 5: cap the registers at 168 so three 128-thread CTAs fit an SM (12 warps instead of 8;
+// measured +3 % at nf = 8; a cap of 128 registers spills and is slower)
+#ifndef PF_FO_MINB
+#define PF_FO_MINB(NF) ((NF) >= 5 ? 3 : 1)
+#endif
+// Consumer: integrates column j of the mode matrix for the k tile bx.  `progress` (may be null)
+// is the producer's published record count in fused launches (pf_fused.cu).
+template <int NF, int NC>
+__device__ __forceinline__ void fo_consume(const FoArgs& a, int64_t bx, int j, const long long* progress) {
+    using S = FoShape<NF>;
+    constexpr int NB = S::NB, SW = S::SW, REC = S::REC, CH = S::CH;
+    const bool pert = a.layout == PF_LAYOUT_PERT;     // perturbation rows only
+    const int NV = pert ? 2 * NF * NF : nvar_of(NF);
+    const int RO = pert ? -NB : 0;                    // row offset of the perturbation block
+    constexpr int KPB = S::BLOCK / (3 - NC);        // k modes per CTA
+
+    __shared__ __align__(128) double srec[2][CH * REC];
+    __shared__ __align__(8) uint64_t bars[2];
+
+    const int tid = threadIdx.x;
+    if (tid >= S::BLOCK) return;                      // fused launches may carry spare threads
+    const int part = (NC == 2) ? 0 : (tid & 1);
+    const int kl = (NC == 2) ? tid : (tid >> 1);
+    const int64_t kk = bx * KPB + kl;
+    const bool live = kk < a.nk;
+    const int64_t nk = a.nk;
+
+    const int64_t nsteps = a.t1 - a.t0;
+    const int64_t nchunks = (nsteps + CH - 1) / CH;
+
+    auto issue = [&](int64_t c) {
+        const int buf = (int)(c & 1);
+        const int64_t base = a.t0 + c * CH;
+        const int64_t cnt = (a.t1 - base) < CH ? (a.t1 - base) : CH;
+        const uint32_t bytes = (uint32_t)(cnt * REC * sizeof(double));
+        if (progress) wait_progress(progress, base + cnt);
+        mbar_expect_tx(&bars[buf], bytes);
+        bulk_g2s(&srec[buf][0], a.rec + base * REC, bytes, &bars[buf]);
+    };
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (nchunks > 0) issue(0);
+        if (nchunks > 1) issue(1);
+    }
+
+    const double kval = live ? a.k[kk] : 0.0;
+    const int64_t ts = live ? a.tsix[kk] : INT64_MAX;
+    const double h = a.h, hh = h * 0.5, h6 = h / 6.0;   // rk4.py:31-32
+    const double nan = qnan();
+
+    double x[NF][NC], v[NF][NC];
+#pragma unroll
+    for (int i = 0; i < NF; ++i)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { x[i][c] = 0.0; v[i][c] = 0.0; }
+
+    if (live && a.t0 > ts) {                          // resume a windowed run
+#pragma unroll
+        for (int i = 0; i < NF; ++i) {
+            const double* sx = a.state + 2 * ((int64_t)(2 * (i * NF + j)) * nk + kk);
+            const double* sv = a.state + 2 * ((int64_t)(2 * (i * NF + j) + 1) * nk + kk);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) { x[i][c] = sx[part + c]; v[i][c] = sv[part + c]; }
+        }
+    }
+
+    int64_t next_out = (a.yout != nullptr && a.out_every > 0) ? a.t0 : INT64_MAX;
+    double* orow = a.yout;                            // start of the current output row block
+
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int buf = (int)(c & 1);
+        mbar_wait(&bars[buf], (uint32_t)((c >> 1) & 1));
+        const int64_t base = a.t0 + c * CH;
+        const int cnt = (int)((a.t1 - base) < CH ? (a.t1 - base) : CH);
+        for (int q = 0; q < cnt; ++q) {
+            const int64_t n = base + q;
+            const double* __restrict__ r = &srec[buf][q * REC];
+            const bool out = (n == next_out);
+            if (n < ts) {
+                // rows before this mode's start stay NaN+NaNj        rk4.py:100
+                if (out && live) {
+                    double nn[NC];
+#pragma unroll
+                    for (int cc = 0; cc < NC; ++cc) nn[cc] = nan;
+                    if (!pert) {
+                        store_row<NC>(orow + 2 * (int64_t)(2 * j) * nk, kk, part, nn);
+                        store_row<NC>(orow + 2 * (int64_t)(2 * j + 1) * nk, kk, part, nn);
+                        if (j == 0) store_row<NC>(orow + 2 * (int64_t)(2 * NF) * nk, kk, part, nn);
+                    }
+#pragma unroll
+                    for (int i = 0; i < NF; ++i) {
+                        const int64_t row = RO + NB + 2 * (i * NF + j);
+                        store_row<NC>(orow + 2 * row * nk, kk, part, nn);
+                        store_row<NC>(orow + 2 * (row + 1) * nk, kk, part, nn);
+                    }
+                }
+            } else {
+                double bgv[3][NC];                    // phi_j, phi'_j, H as this thread stores them
+                if (n == ts) {
+                    // the start row is ystart[:, k] itself                rk4.py:106-107
+                    const double* ys = a.ystart;
+#pragma unroll
+                    for (int i = 0; i < NF; ++i) {
+                        const int64_t row = NB + 2 * (i * NF + j);
+#pragma unroll
+                        for (int cc = 0; cc < NC; ++cc) {
+                            x[i][cc] = ys[2 * (row * nk + kk) + part + cc];
+                            v[i][cc] = ys[2 * ((row + 1) * nk + kk) + part + cc];
+                        }
+                    }
+                    const int rows3[3] = {2 * j, 2 * j + 1, 2 * NF};
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+#pragma unroll
+                        for (int cc = 0; cc < NC; ++cc)
+                            bgv[b][cc] = ys[2 * ((int64_t)rows3[b] * nk + kk) + part + cc];
+                        if (part == 0 && a.flags) {
+                            const double ref = r[S::BG_OFF + rows3[b]];
+                            const double got = bgv[b][0];
+                            if (!(fabs(got - ref) <= 1e-9 * fabs(ref) + 1e-300))
+                                atomicOr(a.flags, PF_FLAG_BG_MISMATCH);
+                        }
+                    }
+                } else {
+                    const int rows3[3] = {2 * j, 2 * j + 1, 2 * NF};
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+                        const double val = r[S::BG_OFF + rows3[b]];
+                        if constexpr (NC == 2) { bgv[b][0] = val; bgv[b][1] = 0.0; }
+                        else { bgv[b][0] = part == 0 ? val : 0.0; }
+                    }
+                }
+                if (out) {
+                    if (!pert) {
+                        store_row<NC>(orow + 2 * (int64_t)(2 * j) * nk, kk, part, bgv[0]);
+                        store_row<NC>(orow + 2 * (int64_t)(2 * j + 1) * nk, kk, part, bgv[1]);
+                        if (j == 0) store_row<NC>(orow + 2 * (int64_t)(2 * NF) * nk, kk, part, bgv[2]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < NF; ++i) {
+                        const int64_t row = RO + NB + 2 * (i * NF + j);
+                        store_row<NC>(orow + 2 * row * nk, kk, part, x[i]);
+                        store_row<NC>(orow + 2 * (row + 1) * nk, kk, part, v[i]);
+                    }
+                }
+                if (n + 1 < a.T) {
+                    // one classical RK4 step n -> n+1                      rk4.py:27-55
+                    double kv[NF][NC], ax[NF][NC], av[NF][NC], xt[NF][NC], vt[NF][NC];
+                    mode_rhs<NF, NC>(r, kval, x, v, kv);
+#pragma unroll
+                    for (int i = 0; i < NF; ++i)
+#pragma unroll
+                        for (int cc = 0; cc < NC; ++cc) {
+                            ax[i][cc] = v[i][cc];
+                            av[i][cc] = kv[i][cc];
+                            xt[i][cc] = fma(hh, v[i][cc], x[i][cc]);
+                            vt[i][cc] = fma(hh, kv[i][cc], v[i][cc]);
+                        }
+                    mode_rhs<NF, NC>(r + SW, kval, xt, vt, kv);
+#pragma unroll
+                    for (int i = 0; i < NF; ++i)
+#pragma unroll
+                        for (int cc = 0; cc < NC; ++cc) {
+                            ax[i][cc] = fma(2.0, vt[i][cc], ax[i][cc]);
+                            av[i][cc] = fma(2.0, kv[i][cc], av[i][cc]);
+                            xt[i][cc] = fma(hh, vt[i][cc], x[i][cc]);
+                            vt[i][cc] = fma(hh, kv[i][cc], v[i][cc]);
+                        }
+                    mode_rhs<NF, NC>(r + 2 * SW, kval, xt, vt, kv);
+#pragma unroll
+                    for (int i = 0; i < NF; ++i)
+#pragma unroll
+                        for (int cc = 0; cc < NC; ++cc) {
+                            ax[i][cc] = fma(2.0, vt[i][cc], ax[i][cc]);
+                            av[i][cc] = fma(2.0, kv[i][cc], av[i][cc]);
+                            xt[i][cc] = fma(h, vt[i][cc], x[i][cc]);
+                            vt[i][cc] = fma(h, kv[i][cc], v[i][cc]);
+                        }
+                    mode_rhs<NF, NC>(r + 3 * SW, kval, xt, vt, kv);
+#pragma unroll
+                    for (int i = 0; i < NF; ++i)
+#pragma unroll
+                        for (int cc = 0; cc < NC; ++cc) {
+                            x[i][cc] = fma(h6, ax[i][cc] + vt[i][cc], x[i][cc]);
+                            v[i][cc] = fma(h6, av[i][cc] + kv[i][cc], v[i][cc]);
+                        }
+                }
+            }
+            if (out) {
+                next_out += a.out_every;
+                orow += 2 * (int64_t)NV * nk;
+            }
+        }
+        __syncthreads();                              // everyone is done reading srec[buf]
+        if (tid == 0 && c + 2 < nchunks) issue(c + 2);
+    }
+
+    if (live && a.state && ts < a.t1) {
+#pragma unroll
+        for (int i = 0; i < NF; ++i) {
+            double* sx = a.state + 2 * ((int64_t)(2 * (i * NF + j)) * nk + kk);
+            double* sv = a.state + 2 * ((int64_t)(2 * (i * NF + j) + 1) * nk + kk);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) { sx[part + c] = x[i][c]; sv[part + c] = v[i][c]; }
+        }
+    }
+}
+
+
+template <int NF, int NC>
+__global__ void __launch_bounds__(FoShape<NF>::BLOCK, PF_FO_MINB(NF)) fo_rk4_kernel(FoArgs a) {
+    fo_consume<NF, NC>(a, blockIdx.x, blockIdx.y, nullptr);
+}
+
+}  // namespace pf

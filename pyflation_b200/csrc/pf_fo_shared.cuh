@@ -52,9 +52,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 
+// Fused launches: records are produced by another CTA of the same grid; wait (acquire) until
+// `need` of them are published, then order the generic-proxy writes before the TMA read.
+__device__ __forceinline__ void wait_progress(const long long* progress, long long need) {
+    long long have;
+    unsigned spins = 0;
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.s64 %0, [%1];" : "=l"(have) : "l"(progress) : "memory");
+        if (have >= need) break;
+        __nanosleep(128);
+        if (++spins > (1u << 27)) __trap();           // ~20 s: the producer died; fail, do not hang
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+
 struct PotParams { double v[PF_MAX_PARAMS]; };
 
 int launch_fo1(const FoArgs& a, cudaStream_t st);   // pf_fo1.cu
+bool launch_fo_fused_generic(const pf_model* m, const FoArgs& a, double simtstart, int64_t n0,
+                             const double* y0_host, double* rec, double* stagey, int32_t* ws,
+                             cudaStream_t st);   // pf_fused.cu (nf = 2)
 bool launch_fo1_fused(const pf_model* m, const FoArgs& a, double simtstart, int64_t n0,
                       const double* y0_host, double* rec, int32_t* ws, cudaStream_t st);
 

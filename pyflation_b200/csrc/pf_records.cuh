@@ -1,0 +1,62 @@
+// Background right-hand side and step-record arithmetic shared by the stand-alone kernels
+// (pf_bg.cu: K1, K1b) and the producer CTA of the fused launch (pf_fused.cu).
+#pragma once
+#include "pf_common.cuh"
+#include "pf_potentials.cuh"
+
+namespace pf {
+
+template <int POT, int NF>
+__device__ __forceinline__ void bg_rhs(const double* __restrict__ p, const double (&y)[2 * NF + 1],
+                                       double (&dy)[2 * NF + 1]) {
+    double phi[NF], dU[NF], d2U[NF * NF], U;
+#pragma unroll
+    for (int i = 0; i < NF; ++i) phi[i] = y[2 * i];
+    potential<POT, NF, false>(p, phi, U, dU, d2U);
+    const double H = y[2 * NF];
+    const double invH2 = 1.0 / (H * H);
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+        const double pd = y[2 * i + 1];
+        dy[2 * i] = pd;                                   // cosmomodels.py:563
+        dy[2 * i + 1] = -(U * pd + dU[i]) * invH2;        // :566
+        s += pd * pd;
+    }
+    dy[2 * NF] = -0.5 * s * H;                            // :569
+}
+
+// One (step n, stage s) entry of a step record from the RK4 stage argument `y` of the background:
+// A = U/H^2, R = 1/(aH), C = M/H^2 (cosmomodels.py:637-674); stage 0 also stores the background
+// row itself, stage 3 the padding word.  Layout: include/pyflation_b200.h (pf_stage_table).
+template <int POT, int NF>
+__device__ __forceinline__ void stage_record(const double* __restrict__ par, double ainit,
+                                             double simtstart, double h, int64_t n, int s,
+                                             const double (&y)[2 * NF + 1], double* __restrict__ r) {
+    constexpr int NB = 2 * NF + 1, REC = rec_of(NF), SW = 2 + NF * NF, BG = 4 * SW;
+    const double x = simtstart + (double)n * h;           // rk4.py:118 last_x
+    const double t = (s == 0) ? x : ((s == 3) ? x + h : x + h * 0.5);
+    const double a = ainit * exp(t);                      // cosmomodels.py:637
+    double phi[NF], pd[NF], dU[NF], d2U[NF * NF], U;
+#pragma unroll
+    for (int i = 0; i < NF; ++i) { phi[i] = y[2 * i]; pd[i] = y[2 * i + 1]; }
+    potential<POT, NF, true>(par, phi, U, dU, d2U);
+    const double H = y[2 * NF];
+    const double invH2 = 1.0 / (H * H);
+    double* o = r + s * SW;
+    o[0] = U * invH2;                                     // A  (:673  U*y'/H**2)
+    o[1] = 1.0 / (a * H);                                 // R  (:673  k/(a*H))
+#pragma unroll
+    for (int i = 0; i < NF; ++i)
+#pragma unroll
+        for (int l = 0; l < NF; ++l)                      // :667-669 and /H**2 at :674
+            o[2 + i * NF + l] =
+                (d2U[i * NF + l] + pd[i] * dU[l] + dU[i] * pd[l] + pd[i] * pd[l] * U) * invH2;
+    if (s == 0) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) r[BG + c] = y[c];
+    }
+    if (s == 3 && (NB + 4 * SW) < REC) r[REC - 1] = 0.0;
+}
+
+}  // namespace pf

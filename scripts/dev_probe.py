@@ -33,6 +33,11 @@ def main(pot="lambdaphi4", nf=1, nk=2**16, bgy=(25.0, 0.0, 0.0), params=None):
         ms = e0.elapsed_time(e1)
         print("K2 %.3f ms  %.3e mode-steps/s  write %.1f GB/s (all rows) %.1f GB/s (active)  %.2f TFLOP/s" % (
             ms, steps / ms * 1e3, out.numel() * 16 / ms / 1e6, steps * 16 * prob.nvar / every / ms / 1e6, steps * flops / ms / 1e9))
+    for rep in range(3):
+        e0, e1 = ev(), ev()
+        e0.record(); prob.solve(y0, n0, T, out, every); e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        print("SOLVE every=%d (K1+K1b+K2) %.3f ms  %.3e mode-steps/s" % (every, ms, steps / ms * 1e3))
     if every != 1 or nf != 1:
         prob.check_flags(); return
     if os.environ.get("PF_FILL_PROBE"):

@@ -216,6 +216,24 @@ def test_fused_solve_equals_separate_kernels():
     assert np.array_equal(host.view(np.float64), fused.view(np.float64), equal_nan=True)
 
 
+def test_fused_solve_two_fields():
+    """nf = 2: the generic producer/consumer launch (pf_fused.cu) against the three separate
+    kernels, full trajectory and strided output."""
+    from pyflation_b200 import engine
+    g = load_fo("c3_hybridquadratic_2p20")
+    m, prob = _problem(g, k=np.linspace(KMIN, KMAX, 1500))
+    y0 = np.real(m.foystart[0:5, 0])
+    n0 = int(m.fotstartindex.min())
+    pm = engine.make_model(m.potential_func, m.pot_params, 2, m.ainit)
+    for every in (1, 9):
+        separate = engine.first_order_device(prob, out_every=every).cpu().numpy()
+        prob2 = engine.FirstOrderProblem(pm, m.k, m.fotstartindex, m.foystart, 0.0, prob.T, 0.01)
+        fused = engine.first_order_device(prob2, out_every=every, y0=y0, n0=n0).cpu().numpy()
+        prob2.check_flags()
+        assert rel_err(fused[:, :5], separate[:, :5]) < 1e-13
+        assert mode_rel_err(fused, separate, 2) < 1e-12
+
+
 def test_linearity_and_column_independence():
     """The perturbation equations are linear with real coefficients: scaling a column's start
     vector by 4 (exact in binary) scales its trajectory by 4 bit-for-bit; a column's result
