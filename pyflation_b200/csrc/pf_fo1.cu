@@ -4,8 +4,8 @@
 // (profiles/r1_k2_*): the kernel is bound by how fast one SM can retire store-carrying steps,
 // so the per-step instruction count and the CTA shape matter more than raw occupancy.
 //
-//   * a thread owns KPT adjacent modes (4*KPT doubles of state); the 16-double step record is
-//     read once per thread with eight 128-bit broadcast shared loads and reused for KPT modes;
+//   * a thread owns one mode (4 doubles of state); the 16-double step record is read with
+//     eight 128-bit broadcast shared loads;
 //   * three row regimes per CTA, all CTA-uniform branches: rows before the CTA's first start
 //     (pure NaN stores, no record traffic), the few rows where some modes of the CTA have
 //     started and some have not (predicated path), and the steady state (no predicates);
@@ -67,21 +67,29 @@ __device__ __forceinline__ void rk4_mode(const Coef& c, double kval, double h, d
     }
 }
 
-// Consumer: integrates the modes of logical CTA `cta` (nthreads threads, KPT modes each).
+// Consumer: integrates the modes of logical CTA `cta` (nthreads threads, one mode each; two
+// modes per thread were measured 1.8x slower: the kernel needs its >= 14 warps per SM).
 // `progress` (may be null) is the producer's published record count in fused launches.
-template <int KPT, bool PERT>
+struct Fo1Smem {                                      // one per CTA, owned by the kernel
+    alignas(128) double srec[2][FO1_CH * FO1_REC];
+    alignas(8) uint64_t bars[2];
+    long long tsmin, tsmax;
+};
+
+template <bool PERT>
 __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nthreads,
-                                            const long long* progress) {
+                                            const long long* progress, Fo1Smem& sm) {
     constexpr int NV = PERT ? 2 : 5;                  // rows per time step in the output
     constexpr int XO = PERT ? 0 : 3;                  // row of dphi within a time step
-    __shared__ __align__(128) double srec[2][FO1_CH * FO1_REC];
-    __shared__ __align__(8) uint64_t bars[2];
-    __shared__ long long s_tsmin, s_tsmax;
+    double (&srec)[2][FO1_CH * FO1_REC] = sm.srec;
+    uint64_t (&bars)[2] = sm.bars;
+    long long& s_tsmin = sm.tsmin;
+    long long& s_tsmax = sm.tsmax;
 
     const int tid = threadIdx.x;
     if (tid >= nthreads) return;                      // fused launches may carry spare threads
     const int64_t nk = a.nk;
-    const int64_t kk0 = (cta * nthreads + tid) * KPT;
+    const int64_t kk = cta * nthreads + tid;
 
     if (tid == 0) {
         s_tsmin = INT64_MAX;
@@ -92,23 +100,17 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
     }
     __syncthreads();
 
-    double kval[KPT], x[KPT][2], v[KPT][2];
-    int64_t ts[KPT];
-    bool live[KPT];
-#pragma unroll
-    for (int m = 0; m < KPT; ++m) {
-        live[m] = (kk0 + m) < nk;
-        kval[m] = live[m] ? a.k[kk0 + m] : 0.0;
-        ts[m] = live[m] ? a.tsix[kk0 + m] : INT64_MAX;
-        x[m][0] = x[m][1] = v[m][0] = v[m][1] = 0.0;
-        if (live[m]) {
-            atomicMin(&s_tsmin, (long long)ts[m]);
-            atomicMax(&s_tsmax, (long long)ts[m]);
-            if (a.t0 > ts[m]) {                               // resume a windowed run
-                const double2 sx = reinterpret_cast<const double2*>(a.state)[kk0 + m];
-                const double2 sv = reinterpret_cast<const double2*>(a.state)[nk + kk0 + m];
-                x[m][0] = sx.x; x[m][1] = sx.y; v[m][0] = sv.x; v[m][1] = sv.y;
-            }
+    const bool live = kk < nk;
+    const double kval = live ? a.k[kk] : 0.0;
+    const int64_t ts = live ? a.tsix[kk] : INT64_MAX;
+    double x[2] = {0.0, 0.0}, v[2] = {0.0, 0.0};
+    if (live) {
+        atomicMin(&s_tsmin, (long long)ts);
+        atomicMax(&s_tsmax, (long long)ts);
+        if (a.t0 > ts) {                                      // resume a windowed run
+            const double2 sx = reinterpret_cast<const double2*>(a.state)[kk];
+            const double2 sv = reinterpret_cast<const double2*>(a.state)[nk + kk];
+            x[0] = sx.x; x[1] = sx.y; v[0] = sv.x; v[1] = sv.y;
         }
     }
     __syncthreads();
@@ -116,26 +118,23 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
     if (tsmin == INT64_MAX) return;                           // CTA past the end of the batch
 
     const double h = a.h, hh = h * 0.5, h6 = h / 6.0;         // rk4.py:31-32
-    const double nan = qnan();
-    double2* prow = reinterpret_cast<double2*>(a.yout) + kk0; // row t0, var 0, this thread's k
+    const double2 nan2 = make_double2(qnan(), qnan());
+    double2* prow = reinterpret_cast<double2*>(a.yout) + kk;  // row t0, var 0, this thread's k
     const int64_t rstride = NV * nk;
 
-    // ---- regime 1: rows before any mode of this CTA starts: NaN+NaNj, no records needed
-    // rows are stored when (n - t0) is a multiple of out_every (0: never); next_out tracks it
+    // ---- regime 1: rows before any mode of this CTA starts: NaN+NaNj, no records needed.
+    // Rows are stored when (n - t0) is a multiple of out_every (0: never); next_out tracks it.
     const int64_t every = a.out_every;
     int64_t next_out = (a.yout != nullptr && every > 0) ? a.t0 : INT64_MAX;
-    int64_t n = a.t0;
     const int64_t nan_end = tsmin < a.t1 ? tsmin : a.t1;
     for (; next_out < nan_end; next_out += every) {
+        if (live) {
 #pragma unroll
-        for (int m = 0; m < KPT; ++m)
-            if (live[m]) {
-#pragma unroll
-                for (int var = 0; var < NV; ++var) __stcs(prow + var * nk + m, make_double2(nan, nan));
-            }
+            for (int var = 0; var < NV; ++var) __stcs(prow + var * nk, nan2);
+        }
         prow += rstride;
     }
-    n = nan_end;
+    int64_t n = nan_end;
     if (n >= a.t1) return;
 
     // ---- regimes 2 and 3: records streamed through shared memory from row c0 on
@@ -166,42 +165,32 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
             const bool out = (n == next_out);
             if (n > tsmax) {
                 // ---- regime 3: every mode of the CTA is running
-#pragma unroll
-                for (int m = 0; m < KPT; ++m)
-                    if (live[m] && out) {
-                        if constexpr (!PERT) {
-                            __stcs(prow + m, make_double2(cf.bg[0], 0.0));
-                            __stcs(prow + nk + m, make_double2(cf.bg[1], 0.0));
-                            __stcs(prow + 2 * nk + m, make_double2(cf.bg[2], 0.0));
-                        }
-                        __stcs(prow + XO * nk + m, make_double2(x[m][0], x[m][1]));
-                        __stcs(prow + (XO + 1) * nk + m, make_double2(v[m][0], v[m][1]));
+                if (live && out) {
+                    if constexpr (!PERT) {
+                        __stcs(prow, make_double2(cf.bg[0], 0.0));
+                        __stcs(prow + nk, make_double2(cf.bg[1], 0.0));
+                        __stcs(prow + 2 * nk, make_double2(cf.bg[2], 0.0));
                     }
-                if (n + 1 < a.T) {
-#pragma unroll
-                    for (int m = 0; m < KPT; ++m) rk4_mode(cf, kval[m], h, hh, h6, x[m], v[m]);
+                    __stcs(prow + XO * nk, make_double2(x[0], x[1]));
+                    __stcs(prow + (XO + 1) * nk, make_double2(v[0], v[1]));
                 }
-            } else {
+                if (n + 1 < a.T) rk4_mode(cf, kval, h, hh, h6, x, v);
+            } else if (live) {
                 // ---- regime 2: some modes of the CTA have started, some have not
+                if (n < ts) {
+                    if (out) {
 #pragma unroll
-                for (int m = 0; m < KPT; ++m) {
-                    if (!live[m]) continue;
-                    if (n < ts[m]) {
-                        if (out) {
-#pragma unroll
-                            for (int var = 0; var < NV; ++var)
-                                __stcs(prow + var * nk + m, make_double2(nan, nan));   // rk4.py:100
-                        }
-                        continue;
+                        for (int var = 0; var < NV; ++var) __stcs(prow + var * nk, nan2);   // rk4.py:100
                     }
+                } else {
                     double2 b0 = make_double2(cf.bg[0], 0.0), b1 = make_double2(cf.bg[1], 0.0),
                             b2 = make_double2(cf.bg[2], 0.0);
-                    if (n == ts[m]) {
+                    if (n == ts) {
                         // the start row is ystart[:, k] itself            rk4.py:106-107
-                        const double2* ys = reinterpret_cast<const double2*>(a.ystart) + kk0 + m;
+                        const double2* ys = reinterpret_cast<const double2*>(a.ystart) + kk;
                         b0 = ys[0]; b1 = ys[nk]; b2 = ys[2 * nk];
                         const double2 sx = ys[3 * nk], sv = ys[4 * nk];
-                        x[m][0] = sx.x; x[m][1] = sx.y; v[m][0] = sv.x; v[m][1] = sv.y;
+                        x[0] = sx.x; x[1] = sx.y; v[0] = sv.x; v[1] = sv.y;
                         if (a.flags) {
                             const bool bad = !(fabs(b0.x - cf.bg[0]) <= 1e-9 * fabs(cf.bg[0]) + 1e-300) ||
                                              !(fabs(b1.x - cf.bg[1]) <= 1e-9 * fabs(cf.bg[1]) + 1e-300) ||
@@ -211,14 +200,14 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
                     }
                     if (out) {
                         if constexpr (!PERT) {
-                            __stcs(prow + m, b0);
-                            __stcs(prow + nk + m, b1);
-                            __stcs(prow + 2 * nk + m, b2);
+                            __stcs(prow, b0);
+                            __stcs(prow + nk, b1);
+                            __stcs(prow + 2 * nk, b2);
                         }
-                        __stcs(prow + XO * nk + m, make_double2(x[m][0], x[m][1]));
-                        __stcs(prow + (XO + 1) * nk + m, make_double2(v[m][0], v[m][1]));
+                        __stcs(prow + XO * nk, make_double2(x[0], x[1]));
+                        __stcs(prow + (XO + 1) * nk, make_double2(v[0], v[1]));
                     }
-                    if (n + 1 < a.T) rk4_mode(cf, kval[m], h, hh, h6, x[m], v[m]);
+                    if (n + 1 < a.T) rk4_mode(cf, kval, h, hh, h6, x, v);
                 }
             }
             if (out) {
@@ -230,19 +219,16 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
         if (tid == 0 && c + 2 < nchunks) issue(c + 2);
     }
 
-    if (a.state) {
-#pragma unroll
-        for (int m = 0; m < KPT; ++m)
-            if (live[m] && ts[m] < a.t1) {
-                reinterpret_cast<double2*>(a.state)[kk0 + m] = make_double2(x[m][0], x[m][1]);
-                reinterpret_cast<double2*>(a.state)[nk + kk0 + m] = make_double2(v[m][0], v[m][1]);
-            }
+    if (a.state && live && ts < a.t1) {
+        reinterpret_cast<double2*>(a.state)[kk] = make_double2(x[0], x[1]);
+        reinterpret_cast<double2*>(a.state)[nk + kk] = make_double2(v[0], v[1]);
     }
 }
 
 template <bool PERT>
 __global__ void __launch_bounds__(512) fo1_kernel(FoArgs a) {
-    fo1_consume<1, PERT>(a, blockIdx.x, blockDim.x, nullptr);
+    __shared__ Fo1Smem sm;
+    fo1_consume<PERT>(a, blockIdx.x, blockDim.x, nullptr, sm);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -371,8 +357,9 @@ __global__ void __launch_bounds__(512) fo1_fused_kernel(FoArgs a, ProdArgs f, in
         return;
     }
     const long long* progress = reinterpret_cast<const long long*>(f.ws + 2);
-    if (a.layout == PF_LAYOUT_PERT) fo1_consume<1, true>(a, cta - 1, cthreads, progress);
-    else fo1_consume<1, false>(a, cta - 1, cthreads, progress);
+    __shared__ Fo1Smem sm;
+    if (a.layout == PF_LAYOUT_PERT) fo1_consume<true>(a, cta - 1, cthreads, progress, sm);
+    else fo1_consume<false>(a, cta - 1, cthreads, progress, sm);
 }
 
 // Grid shape: a whole number c of CTAs per SM, c the smallest for which a CTA holds at most

@@ -42,7 +42,8 @@ def load_fo(name):
     for key, val in zip(d["param_keys"], d["param_vals"]):
         params[str(key)] = int(val) if str(key) == "nfields" else float(val)
     d["params"] = params
-    d["extra"] = {str(key): int(val) for key, val in zip(d["extra_keys"], d["extra_vals"])}
+    d["extra"] = {str(key): (int(val) if str(key) == "suppress_ix" else float(val))
+                  for key, val in zip(d["extra_keys"], d["extra_vals"])}
     return d
 
 

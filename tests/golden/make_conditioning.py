@@ -49,6 +49,7 @@ def main():
         g = load_fo(name)
         nf = g["nfields"]
         kw = variant_kwargs(g)
+        kw.update(cq=float(g["cq"]), tend=float(g["tend"]), h=float(g["h"]))
         a = O.first_order_run(g["potential"], g["k"], nf, g["params"], g["bgystart"].copy(),
                               integrate=False, **kw)
         y0 = g["bgystart"].copy()

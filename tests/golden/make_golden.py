@@ -85,6 +85,9 @@ FIXTURES = {
                    "FOCanonicalTwoStage", {}),
     "hilltopaxion": ("hilltopaxion", 2, {}, [17.0, -0.1, 0.45, 0.0, 0], 2 ** 10, 5, 50,
                      "FOCanonicalTwoStage", {}),
+    # non-default step size / sub-horizon factor / end time (T = around((tend-simtstart)/h)+1)
+    "nondefault_steps": ("msqphisq", 1, {"nfields": 1}, [18.0, -0.1, 0], "K4", 5, 25,
+                         "FOCanonicalTwoStage", {"tstep_wanted": 0.02, "cq": 40, "tend": 82.0}),
     # initial-condition variants (cosmomodels.py:2017-2197)
     "ic_fixedainit": ("msqphisq", 1, {"nfields": 1}, [18.0, -0.1, 0], "K4", 5, 50,
                       "FixedainitTwoStage", {}),
@@ -144,7 +147,8 @@ def make_fo(ref, name):
         param_vals=np.array([float(params[q]) for q in sorted(params.keys())]),
         bgystart=np.array(m.bgystart, dtype=float), extra_keys=np.array(sorted(extra.keys())),
         extra_vals=np.array([float(extra[q]) for q in sorted(extra.keys())]),
-        grid=str(grid), kix=kix, k=k, cq=50.0, tend=83.0, h=0.01, simtstart=0.0,
+        grid=str(grid), kix=kix, k=k, cq=float(m.cq), tend=float(m.tend), h=float(m.tstep_wanted),
+        simtstart=0.0,
         T=T, rows=rows, tresult=m.tresult, yrows=m.yresult[rows],
         bgT=bgT, bgrows=bgrows, bgyrows=m.bgmodel.yresult[bgrows],
         bgepsilon_rows=m.bgepsilon[bgrows],

@@ -60,7 +60,7 @@ def test_first_order_stage_matches_reference_golden(name):
     tol_bg, _, _ = tolerances(name)
     fo = c.CanonicalFirstOrder(ystart=g["foystart"].copy(), tstart=g["fotstart"], simtstart=0.0,
                                tstartindex=g["fotstartindex"], tend=float(g["fotend"]),
-                               tstep_wanted=0.01, solver="rkdriver_tsix", k=g["k"],
+                               tstep_wanted=float(g["h"]), solver="rkdriver_tsix", k=g["k"],
                                ainit=g["ainit"], potential_func=g["potential"],
                                pot_params=dict(g["params"]), nfields=nf)
     fo.run(saveresults=False)

@@ -23,7 +23,8 @@ def oracle_run(oracle, g, integrate=True):
     if g["cls"] == "FixedainitTwoStage":
         kw["fixed_ainit"] = 7.837219134630212e-65          # cosmomodels.py:2043
     return oracle.first_order_run(g["potential"], g["k"], g["nfields"], g["params"],
-                                  g["bgystart"].copy(), integrate=integrate, **kw)
+                                  g["bgystart"].copy(), cq=float(g["cq"]), tend=float(g["tend"]),
+                                  h=float(g["h"]), integrate=integrate, **kw)
 
 
 @pytest.mark.parametrize("name", fo_fixture_names())
