@@ -484,3 +484,33 @@ def test_derivs_method_matches_oracle(oracle, pot, nf, params):
     yb = np.real(y[:nb, :1]).copy()
     np.testing.assert_allclose(bg.derivs(yb, t), oracle.make_bg_rhs(pot, params, nf)(yb, t), rtol=1e-12)
     assert bg.derivs(yb[:, 0], t).shape == (nb,)
+
+
+def test_nonzero_simtstart_and_late_background_start(oracle):
+    """rkdriver_tsix arguments the two-stage driver never varies: a simulation clock that does
+    not start at zero (a = ainit*exp(t) shifts, rk4.py:116-118) and a background run that
+    starts at a later row (NaN rows before it, rk4.py:95-107).  Checked against the oracle."""
+    from pyflation_b200 import cosmomodels as c
+    g = load_fo("c1_msqphisq_k4")
+    sel = [0, 7, 19, 32]
+    k, tsix, y0 = g["k"][sel], g["fotstartindex"][sel], g["foystart"][:, sel].copy()
+    s0, h = 0.37, 0.01
+    tend = float(g["fotend"]) + s0
+    want_t, want = oracle.rk4_drive(y0, s0, tsix, tend, h, oracle.make_fo_rhs("msqphisq", {}, 1, k, g["ainit"]))
+    fo = c.CanonicalFirstOrder(ystart=y0, tstart=g["fotstart"][sel] + s0, simtstart=s0, tstartindex=tsix,
+                               tend=tend, tstep_wanted=h, k=k, ainit=g["ainit"], potential_func="msqphisq")
+    fo.run(saveresults=False)
+    assert np.array_equal(fo.tresult, want_t)
+    assert rel_err(fo.yresult[:, :3], want[:, :3]) < TOL
+    assert mode_rel_err(fo.yresult, want, 1) < TOL
+    # background alone, started at row 40 of a 0.02-step grid
+    yb = np.array([17.0, -0.12, 0.0])
+    bg = c.CanonicalBackground(ystart=yb.copy(), tstartindex=np.array([40]), tend=30.0, tstep_wanted=0.02,
+                               potential_func="lambdaphi4")
+    bg.run(saveresults=False)
+    wt, wy = oracle.rk4_drive(bg.ystart.copy(), 0.0, np.array([40]), 30.0, 0.02,
+                              oracle.make_bg_rhs("lambdaphi4", {}, 1))
+    assert bg.yresult.shape == wy.shape == (1501, 3, 1) and bg.yresult.dtype == np.float64
+    assert np.isnan(bg.yresult[:40]).all() and np.array_equal(bg.yresult[40, :, 0], bg.ystart)
+    assert np.array_equal(bg.tresult, wt)
+    assert rel_err(bg.yresult, wy) < 1e-12
