@@ -379,10 +379,12 @@ def run_e2e(args, m, T, nvar, mode_steps, world, rank, barrier):
         last = host[T - 1].numpy()
         assert np.isfinite(last[3:]).all()
     h2d = int(ystart_host.size * 16 + m.k.size * 8 + tsix_host.size * 8)
+    moved = dict(rk4.last_transfer)
     # full layout: every row crosses PCIe; compact (default when the host can hold the result):
     # the 2 perturbation rows of every time step + the 1 MB step-record table cross, the 3
     # background rows are rebuilt on the host by pf_host_fill_background
-    d2h = int(need) if not full else int(T * 2 * NK_PER_GPU * 16 + T * 16 * 8)
+    # (columns that have not started yet in a time window are skipped as well)
+    d2h = int(need) if not full else int(moved["d2h_bytes"])
     return {"value": float(ww[0]) * nsteps / float(tt[0]), "unit": UNIT,
             "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
             "host_result_bytes_per_step": int(need) * world, "steps": nsteps,

@@ -193,13 +193,16 @@ int pf_pr_spectrum(int nfields, int64_t nrows, int64_t nk, const double *y_dev,
  * pf_host_fill_background: host threads write rows [0, 2nf+1) of yresult[t0:t1] -- NaN+NaNj
  * before a mode's start row, ystart[:,k] at it (bit for bit, rk4.py:106-107), (bg[t][v], 0)
  * after it.  bg_host is [T][bg_pitch] doubles with the background row at column bg_off
- * (pass the step records: bg_pitch = pf_rec_doubles(nf), bg_off = 4(2+nf^2)).  Streaming
- * (non-temporal) stores; nthreads <= 0 picks the hardware concurrency. */
+ * (pass the step records: bg_pitch = pf_rec_doubles(nf), bg_off = 4(2+nf^2)).  pert_nan != 0
+ * also writes the NaN prefix of the perturbation rows (t < tsix_k), so that the device->host
+ * copies may skip columns that have not started.  Streaming (non-temporal) stores; nthreads <= 0
+ * picks the hardware concurrency. */
 int pf_copy_rows_d2h(void *dst_host, size_t dst_pitch, const void *src_dev, size_t src_pitch,
                      size_t width_bytes, size_t height, void *stream);
 int pf_host_fill_background(double *yout_host, int nfields, int64_t nk, int64_t t0, int64_t t1,
                             const double *bg_host, int64_t bg_pitch, int64_t bg_off,
-                            const int64_t *tsix_host, const double *ystart_host, int nthreads);
+                            const int64_t *tsix_host, const double *ystart_host, int pert_nan,
+                            int nthreads);
 
 /* ---- gather helper for the k-sharded multi-GPU layout ----
  * Interleave a rank's slab [nrows][nvar][nk_r] into the global layout [nrows][nvar][nk] at

@@ -90,7 +90,7 @@ def lib():
     c_sz = ctypes.c_size_t
     L.pf_copy_rows_d2h.argtypes = [c_vp, c_sz, c_vp, c_sz, c_sz, c_sz, c_vp]
     L.pf_host_fill_background.argtypes = [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64,
-                                          c_vp, c_vp, c_int]
+                                          c_vp, c_vp, c_int, c_int]
     L.pf_pr_spectrum.argtypes = [c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]
     L.pf_scatter_slab.argtypes = [c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]
     L.pf_crossing_rows.argtypes = [c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]

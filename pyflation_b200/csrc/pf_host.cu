@@ -16,8 +16,10 @@ namespace pf {
 // background rows (2nf+1 independent non-temporal store streams).
 template <int NB>
 static void fill_rows_nb(double* yout, int nvar, int64_t nk, int64_t ta, int64_t tb, const double* bg,
-                         int64_t bg_pitch, int64_t bg_off, const int64_t* tsix, const double* ystart) {
+                         int64_t bg_pitch, int64_t bg_off, const int64_t* tsix, const double* ystart,
+                         bool pert_nan) {
     const __m128d nan2 = _mm_set1_pd(NAN);
+    const int nan_rows = pert_nan ? nvar : NB;          // rows NaN-filled before a mode's start
     for (int64_t t = ta; t < tb; ++t) {
         __m128d val[NB];
         double* row[NB];
@@ -30,7 +32,7 @@ static void fill_rows_nb(double* yout, int nvar, int64_t nk, int64_t ta, int64_t
             if (t > s) {
                 for (int v = 0; v < NB; ++v) _mm_stream_pd(row[v] + 2 * k, val[v]);
             } else if (t < s) {
-                for (int v = 0; v < NB; ++v) _mm_stream_pd(row[v] + 2 * k, nan2);
+                for (int v = 0; v < nan_rows; ++v) _mm_stream_pd(row[0] + 2 * ((int64_t)v * nk + k), nan2);
             } else {                                                             // rk4.py:106-107
                 for (int v = 0; v < NB; ++v)
                     _mm_stream_pd(row[v] + 2 * k, _mm_loadu_pd(ystart + 2 * ((int64_t)v * nk + k)));
@@ -42,9 +44,9 @@ static void fill_rows_nb(double* yout, int nvar, int64_t nk, int64_t ta, int64_t
 
 static void fill_rows(double* yout, int nb, int nvar, int64_t nk, int64_t ta, int64_t tb,
                       const double* bg, int64_t bg_pitch, int64_t bg_off, const int64_t* tsix,
-                      const double* ystart) {
+                      const double* ystart, bool pert_nan) {
     switch (nb) {
-#define PF_CASE(N) case N: fill_rows_nb<N>(yout, nvar, nk, ta, tb, bg, bg_pitch, bg_off, tsix, ystart); break;
+#define PF_CASE(N) case N: fill_rows_nb<N>(yout, nvar, nk, ta, tb, bg, bg_pitch, bg_off, tsix, ystart, pert_nan); break;
         PF_CASE(3) PF_CASE(5) PF_CASE(7) PF_CASE(9) PF_CASE(11) PF_CASE(13) PF_CASE(15) PF_CASE(17)
 #undef PF_CASE
         default: break;
@@ -70,7 +72,8 @@ extern "C" int pf_copy_rows_d2h(void* dst_host, size_t dst_pitch, const void* sr
 
 extern "C" int pf_host_fill_background(double* yout_host, int nfields, int64_t nk, int64_t t0, int64_t t1,
                                        const double* bg_host, int64_t bg_pitch, int64_t bg_off,
-                                       const int64_t* tsix_host, const double* ystart_host, int nthreads) {
+                                       const int64_t* tsix_host, const double* ystart_host, int pert_nan,
+                                       int nthreads) {
     if (nfields < 1 || nfields > PF_MAX_NFIELDS) { set_error("pf_host_fill_background: nfields=%d", nfields); return PF_E_NFIELDS; }
     if (nk < 0 || t0 < 0 || t1 < t0) { set_error("pf_host_fill_background: bad sizes"); return PF_E_ARG; }
     if (nk == 0 || t0 == t1) return PF_OK;
@@ -85,7 +88,7 @@ extern "C" int pf_host_fill_background(double* yout_host, int nfields, int64_t n
     for (int w = 0; w < nt; ++w) {
         const int64_t ta = t0 + rows * w / nt, tb = t0 + rows * (w + 1) / nt;
         pool.emplace_back(fill_rows, yout_host, nb, nvar, nk, ta, tb, bg_host, bg_pitch, bg_off, tsix_host,
-                          ystart_host);
+                          ystart_host, pert_nan != 0);
     }
     for (auto& th : pool) th.join();
     return PF_OK;

@@ -16,6 +16,9 @@ from . import engine, _lib
 
 rk_log = logging.getLogger(__name__)
 
+# bytes the last first-order rkdriver_tsix call moved over PCIe (host->device, device->host)
+last_transfer = {"h2d_bytes": 0, "d2h_bytes": 0}
+
 
 class SimRunError(Exception):
     """Generic error for model simulating run. (rk4.py:141)"""
@@ -140,6 +143,7 @@ def _run_first_order(model, ystart, simtstart, tsix, T, h, yresult_out=None, row
         out = yresult_out if torch.is_tensor(yresult_out) else torch.as_tensor(yresult_out)
     res = engine.first_order_host(prob, out=out, y0=np.real(ystart[0:2 * nf + 1, 0]), n0=n0)
     prob.check_flags()
+    last_transfer.update(h2d_bytes=prob.h2d_bytes, d2h_bytes=prob.d2h_bytes)
     return yresult_out if (yresult_out is not None and not torch.is_tensor(yresult_out)) else res.numpy()
 
 

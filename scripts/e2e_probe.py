@@ -26,18 +26,9 @@ def run(label, **kw):
         best = min(best, t2 - t0)
     print("%-40s total %.1f ms (setup %.1f ms)" % (label, best * 1e3, (t1 - t0) * 1e3))
 
-os.environ["PF_E2E_NOFILL"] = "1"
-run("compact, NO fill (copies only)")
-del os.environ["PF_E2E_NOFILL"]
-import ctypes
-from pyflation_b200 import _lib
-rec = np.random.rand(T, 16)
-t0 = time.perf_counter()
-_lib.lib().pf_host_fill_background(ctypes.c_void_p(host.data_ptr()), 1, nk, 0, T, ctypes.c_void_p(rec.ctypes.data), 16, 12,
-                                   ctypes.c_void_p(ts.ctypes.data), ctypes.c_void_p(ys.ctypes.data), 16)
-print("fill alone (16 threads, whole result): %.1f ms" % ((time.perf_counter() - t0) * 1e3))
+for rep in range(2):
+    os.environ["PF_E2E_NOSKIP"] = "1"
+    run("compact, all columns copied")
+    del os.environ["PF_E2E_NOSKIP"]
+    run("compact, unstarted columns skipped")
 run("full layout (all rows over PCIe)", compact=False)
-for nt in (4, 8, 12, 16):
-    run("compact, fill threads=%d" % nt, fill_threads=nt)
-for slab in (256 << 20, 512 << 20, 2 << 30):
-    run("compact, 16 threads, slab=%d MiB" % (slab >> 20), slab_bytes=slab)

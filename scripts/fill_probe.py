@@ -15,7 +15,7 @@ for nt in (1, 4, 8, 12, 16, 24, 32):
     for rep in range(3):
         t0 = time.perf_counter()
         rc = L.pf_host_fill_background(ctypes.c_void_p(out.data_ptr()), 1, nk, 0, T, ctypes.c_void_p(rec.ctypes.data), 16, 12,
-                                       ctypes.c_void_p(tsix.ctypes.data), ctypes.c_void_p(ystart.ctypes.data), nt)
+                                       ctypes.c_void_p(tsix.ctypes.data), ctypes.c_void_p(ystart.ctypes.data), 0, nt)
         best = min(best, time.perf_counter() - t0)
     print("threads %2d: %.1f GB/s (rc %d)" % (nt, T * 3 * nk * 16 / best / 1e9, rc))
 y = out.numpy()

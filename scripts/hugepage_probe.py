@@ -16,7 +16,7 @@ def bench(ptr, label):
     for rep in range(2):
         t0 = time.perf_counter()
         L.pf_host_fill_background(ctypes.c_void_p(ptr), 1, nk, 0, T, ctypes.c_void_p(rec.ctypes.data), 16, 12,
-                                  ctypes.c_void_p(tsix.ctypes.data), ctypes.c_void_p(ys.ctypes.data), 16)
+                                  ctypes.c_void_p(tsix.ctypes.data), ctypes.c_void_p(ys.ctypes.data), 0, 16)
         dt = time.perf_counter() - t0
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for w in range(T // 512):
