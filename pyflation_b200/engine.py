@@ -194,7 +194,7 @@ def plan_window(T, nvar, nk, slab_bytes):
 
 
 def first_order_host(prob, out=None, slab_bytes=1 << 30, ring=None, y0=None, n0=None, compact=True,
-                     fill_threads=0):
+                     fill_threads=0, skip_unstarted=True):
     """Trajectory delivered into host memory.  Time windows ping-pong between two device slabs;
     the device->host copy of window w overlaps the integration of window w+1.
 
@@ -226,8 +226,7 @@ def first_order_host(prob, out=None, slab_bytes=1 << 30, ring=None, y0=None, n0=
     layout = _lib.PF_LAYOUT_PERT if compact else _lib.PF_LAYOUT_FULL
     # start rows sorted in k (the normal case): in every window the started modes are a prefix
     # of the columns, so only that prefix is copied; the host fill writes the NaNs of the rest
-    sorted_starts = bool(compact and np.all(np.diff(prob.tsix_host) >= 0)
-                         and not os.environ.get("PF_E2E_NOSKIP"))
+    sorted_starts = bool(compact and skip_unstarted and np.all(np.diff(prob.tsix_host) >= 0))
     filler = None
     fill_rc = []
     d2h_bytes = 0
@@ -273,7 +272,7 @@ def first_order_host(prob, out=None, slab_bytes=1 << 30, ring=None, y0=None, n0=
                 ev = torch.cuda.Event()
                 ev.record(copier)
             copied[b] = ev
-            if compact and t0 == 0 and not os.environ.get("PF_E2E_NOFILL"):
+            if compact and t0 == 0:
                 # the step records (background rows included) are complete once window 0 is:
                 # bring them over and let the host threads write the background rows of every
                 # time step while the remaining windows compute and copy
