@@ -26,11 +26,22 @@ def run_model(g):
     return m
 
 
+# Full two-stage runs whose RAW complex start vectors are not reproduced to 1e-9: the
+# Bunch-Davies phase k*(eta_* - eta_init) is 1e8..1e11 rad, so a last-bit difference in H (FMA
+# contraction in a potential that is a sum of terms, or CUDA sincos vs libm) becomes a phase
+# offset of this size -- measured values in parentheses (scripts/raw_parity_report.py).  The
+# other 19 fixtures have bit-identical start vectors and raw trajectories within ~1e-14.
+RAW_PHASE_EXCEPTIONS = {"hilltopaxion": 1e-5,      # (5.8e-7)
+                        "hybrid2and4": 1e-3,       # (4.7e-5)
+                        "quartictwofield": 1e-4}   # (1.8e-6)
+
+
 def tolerances(name):
-    """1e-9 unless the reference's own computation is ill-conditioned for this fixture
+    """(background / phase-free tolerance, amplitude tolerance, raw complex tolerance).
+    1e-9 unless the reference's own computation is ill-conditioned for this fixture
     (tests/golden/make_conditioning.py: response of the oracle to a 1-ulp input change)."""
     c = CONDITIONING[name]
-    return (max(TOL, 100 * c["bg"]), max(TOL, 100 * c["amp"]), max(TOL, 100 * c["phase"]))
+    return (max(TOL, 100 * c["bg"]), max(TOL, 100 * c["amp"]), RAW_PHASE_EXCEPTIONS.get(name, TOL))
 
 
 def phase_normalised(y, y0, nf):
@@ -112,6 +123,8 @@ def test_full_two_stage_run_matches_reference_golden(name):
     for col, s in enumerate(m.fotstartindex):
         assert np.array_equal(m.yresult[s, :, col], m.foystart[:, col])
         assert np.isnan(m.yresult[:s, :, col].real).all()
+    # ... and raw, phase included (1e-9 for all but the three documented fixtures)
+    assert mode_rel_err(m.yresult[rows], g["yrows"], nf) < max(tol_phase, tol_bg)
     assert rel_err(m.Pr[-1:], g["Pr_last"]) < tol_bg
     assert rel_err(m.scaled_Pr[-1:], g["scaled_Pr_last"]) < tol_bg
     assert rel_err(m.Pr[rows], g["Pr_rows"]) < tol_bg
