@@ -258,9 +258,8 @@ __device__ __forceinline__ void bg1_rhs(const double* __restrict__ p, double phi
                                         double& dphi, double& dpd, double& dH) {
     double f[1] = {phi}, dU[1], d2U[1], U;
     potential<POT, 1, false>(p, f, U, dU, d2U);
-    const double invH2 = 1.0 / (H * H);
     dphi = pd;                                        // cosmomodels.py:563
-    dpd = -(U * pd + dU[0]) * invH2;                  // :566
+    dpd = -(U * pd + dU[0]) / (H * H);                // :566 (true division, as NumPy's real arrays)
     dH = -0.5 * (pd * pd) * H;                        // :569
 }
 

@@ -9,6 +9,23 @@
 
 namespace pf {
 
+// x^3 and x^4 rounded once (double-double product, then one rounding), like the correctly rounded
+// pow() behind NumPy's  y[0]**3, y[0]**4  (cmpotentials.py:116-118 etc.); (x*x)*(x*x) rounds
+// twice and is off by an ulp in a quarter of the cases, which the Bunch-Davies phase of the
+// first-order start vectors magnifies by 1e8..1e11.
+__device__ __forceinline__ double pow4_cr(double x) {
+    const double p = x * x, e = fma(x, x, -p);          // x^2 = p + e exactly
+    const double hi = p * p;
+    const double lo = fma(p, p, -hi) + 2.0 * (p * e);
+    return hi + lo;
+}
+__device__ __forceinline__ double pow3_cr(double x) {
+    const double p = x * x, e = fma(x, x, -p);
+    const double hi = p * x;
+    const double lo = fma(p, x, -hi) + e * x;
+    return hi + lo;
+}
+
 template <int POT>
 struct PotNF {  // number of fields a potential is defined for (0 = any)
     static constexpr int value =
@@ -30,18 +47,18 @@ __device__ __forceinline__ void potential(const double* __restrict__ p, const do
         if constexpr (D2) d2U[0] = m2;
     } else if constexpr (POT == PF_LAMBDAPHI4) {              // :74-129
         const double l = p[0], f2 = phi[0] * phi[0];
-        U = 0.25 * l * (f2 * f2);
-        dU[0] = l * (f2 * phi[0]);
+        U = 0.25 * l * pow4_cr(phi[0]);
+        dU[0] = l * pow3_cr(phi[0]);
         if constexpr (D2) d2U[0] = 3.0 * l * f2;
     } else if constexpr (POT == PF_LINDE) {                   // :131-199
         const double m2 = p[0] * p[0], l = p[1], f2 = phi[0] * phi[0];
-        U = -0.5 * m2 * f2 + 0.25 * l * (f2 * f2) + (m2 * m2) / (4.0 * l);
-        dU[0] = -m2 * phi[0] + l * (f2 * phi[0]);
+        U = -0.5 * m2 * f2 + 0.25 * l * pow4_cr(phi[0]) + (m2 * m2) / (4.0 * l);
+        dU[0] = -m2 * phi[0] + l * pow3_cr(phi[0]);
         if constexpr (D2) d2U[0] = -m2 + 3.0 * l * f2;
     } else if constexpr (POT == PF_HYBRID2AND4) {             // :201-269
         const double m2 = p[0] * p[0], l = p[1], f2 = phi[0] * phi[0];
-        U = 0.5 * m2 * f2 + 0.25 * l * (f2 * f2);
-        dU[0] = m2 * phi[0] + l * (f2 * phi[0]);
+        U = 0.5 * m2 * f2 + 0.25 * l * pow4_cr(phi[0]);
+        dU[0] = m2 * phi[0] + l * pow3_cr(phi[0]);
         if constexpr (D2) d2U[0] = m2 + 3.0 * l * f2;
     } else if constexpr (POT == PF_PHI2OVER3) {               // :271-326
         const double s = p[0];
@@ -109,9 +126,9 @@ __device__ __forceinline__ void potential(const double* __restrict__ p, const do
     } else if constexpr (POT == PF_QUARTICTWOFIELD) {         // :848-894
         const double a = p[0] * p[0], b = p[1] * p[1], l1 = p[2], l2 = p[3];
         const double f2 = phi[0] * phi[0], c2 = phi[1] * phi[1];
-        U = 0.5 * (a * f2 + 0.5 * l1 * (f2 * f2) + b * c2 + 0.5 * l2 * (c2 * c2));
-        dU[0] = a * phi[0] + l1 * (f2 * phi[0]);
-        dU[1] = b * phi[1] + l2 * (c2 * phi[1]);
+        U = 0.5 * (a * f2 + 0.5 * l1 * pow4_cr(phi[0]) + b * c2 + 0.5 * l2 * pow4_cr(phi[1]));
+        dU[0] = a * phi[0] + l1 * pow3_cr(phi[0]);
+        dU[1] = b * phi[1] + l2 * pow3_cr(phi[1]);
         if constexpr (D2) { d2U[0] = a + 3.0 * l1 * f2; d2U[3] = b + 3.0 * l2 * c2; }
     } else if constexpr (POT == PF_HYBRIDQUARTIC) {           // :896-961
         const double l = p[0], v = p[1], mu = p[2], pc = p[3];

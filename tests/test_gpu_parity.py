@@ -26,14 +26,12 @@ def run_model(g):
     return m
 
 
-# Full two-stage runs whose RAW complex start vectors are not reproduced to 1e-9: the
-# Bunch-Davies phase k*(eta_* - eta_init) is 1e8..1e11 rad, so a last-bit difference in H (FMA
-# contraction in a potential that is a sum of terms, or CUDA sincos vs libm) becomes a phase
-# offset of this size -- measured values in parentheses (scripts/raw_parity_report.py).  The
-# other 19 fixtures have bit-identical start vectors and raw trajectories within ~1e-14.
-RAW_PHASE_EXCEPTIONS = {"hilltopaxion": 1e-5,      # (5.8e-7)
-                        "hybrid2and4": 1e-3,       # (4.7e-5)
-                        "quartictwofield": 1e-4}   # (1.8e-6)
+# The background kernel rounds like NumPy (no FMA contraction, true division, x**3 / x**4
+# rounded once), so the full two-stage run reproduces the reference's start vectors BIT FOR BIT
+# for every fixture -- which matters because the Bunch-Davies phase k*(eta_* - eta_init) is
+# 1e8..1e11 rad and turns a last-bit difference in H into a 1e-6..1e-4 phase offset
+# (scripts/raw_parity_report.py; before that change three fixtures showed exactly this).
+RAW_PHASE_EXCEPTIONS = {}
 
 
 def tolerances(name):
@@ -114,6 +112,7 @@ def test_full_two_stage_run_matches_reference_golden(name):
     assert rel_err(m.foystart[:nb], g["foystart"][:nb]) < tol_bg
     assert rel_err(np.abs(m.foystart[nb:]), np.abs(g["foystart"][nb:]), 1e-200) < tol_amp
     assert rel_err(m.foystart[nb:], g["foystart"][nb:], 1e-200) < tol_phase
+    assert np.array_equal(m.foystart[nb:], g["foystart"][nb:])  # in fact bit-identical mode vectors
     assert rel_err(m.tresult, g["tresult"]) == 0.0
     rows = g["rows"]
     got = phase_normalised(m.yresult[rows], m.foystart, nf)
@@ -123,7 +122,7 @@ def test_full_two_stage_run_matches_reference_golden(name):
     for col, s in enumerate(m.fotstartindex):
         assert np.array_equal(m.yresult[s, :, col], m.foystart[:, col])
         assert np.isnan(m.yresult[:s, :, col].real).all()
-    # ... and raw, phase included (1e-9 for all but the three documented fixtures)
+    # ... and raw, phase included
     assert mode_rel_err(m.yresult[rows], g["yrows"], nf) < max(tol_phase, tol_bg)
     assert rel_err(m.Pr[-1:], g["Pr_last"]) < tol_bg
     assert rel_err(m.scaled_Pr[-1:], g["scaled_Pr_last"]) < tol_bg
