@@ -422,6 +422,25 @@ def test_device_potentials_match_reference():
     assert len(seen) == 18
 
 
+def test_model_pr_property_uses_device_reduce():
+    """m.Pr over a whole (host) trajectory goes through K5 in chunks and equals the NumPy path."""
+    from pyflation_b200.analysis import adiabatic
+    g = load_fo("c3_hybridquadratic_2p20")
+    gg = dict(g)
+    gg["k"] = np.linspace(KMIN, KMAX, 700)
+    m = run_model(gg)
+    assert m.yresult.nbytes > adiabatic._DEVICE_REDUCE_BYTES
+    dev = m.Pr
+    old, adiabatic._DEVICE_REDUCE_BYTES = adiabatic._DEVICE_REDUCE_BYTES, 1 << 60
+    try:
+        host = m.Pr
+    finally:
+        adiabatic._DEVICE_REDUCE_BYTES = old
+    assert rel_err(dev, host) < 1e-13
+    small = adiabatic._pr_on_device(m.yresult[-5:], 2, chunk_bytes=1 << 20)
+    assert rel_err(small, host[-5:]) < 1e-13
+
+
 def test_pr_kernel_known_answers():
     """K5 against the reference's hand-computed P_R vectors (test_adiabatic.py:155-260)."""
     import torch
