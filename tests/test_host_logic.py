@@ -203,3 +203,47 @@ def test_bench_reference_arm_on_cpu():
     assert "2 processes x 16 consecutive modes" in arm.sample
     cfg = bench.workload_config(1)
     assert cfg["nk_per_gpu"] == 2 ** 16 and cfg["potential"] == "lambdaphi4"
+
+
+def test_crossing_rows_property(oracle):
+    """Property test (hypothesis): for arbitrary positive, not necessarily monotone a*H and any k
+    inside its range, the searchsorted-on-running-maximum crossing equals the reference's scan."""
+    from hypothesis import given, settings, strategies as st
+    from pyflation_b200 import cosmomodels as c
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(5, 200), st.integers(1, 40), st.integers(0, 2 ** 31 - 1))
+    def check(T, nk, seed):
+        rng = np.random.RandomState(seed)
+        t = np.arange(T) * 0.01
+        H = np.exp(rng.uniform(-12, -9, T))                      # wild, non-monotone
+        m = c.FOCanonicalTwoStage(k=np.array([1.0]), nfields=1)
+        m.ainit = 10.0 ** rng.uniform(-70, -50)
+        aH = 50 * m.ainit * np.exp(t) * H
+        k = np.sort(rng.uniform(aH.min() * 0.5, aH.max() * 0.999, nk))
+        m.k = k
+        want_rows, want_t = oracle.crossing_indices(k, t, H, m.ainit, 50)
+        got = m.findallkcrossings(t, H)
+        assert np.array_equal(got[:, 0].astype(int), want_rows)
+        assert np.array_equal(got[:, 1], want_t)
+
+    check()
+
+
+def test_partition_property():
+    """Property test: contiguous partitions cover the range, are monotone, and no slab exceeds
+    the ideal share by more than one item's cost."""
+    from hypothesis import given, settings, strategies as st
+    from pyflation_b200 import parallel
+
+    @settings(max_examples=100, deadline=None)
+    @given(st.integers(1, 300), st.integers(1, 16), st.integers(0, 2 ** 31 - 1))
+    def check(n, world, seed):
+        cost = np.random.RandomState(seed).uniform(0.5, 2.0, n)
+        b = parallel.partition_contiguous(cost, world)
+        assert b[0] == 0 and b[-1] == n and len(b) == world + 1 and np.all(np.diff(b) >= 0)
+        per = np.array([cost[b[r]:b[r + 1]].sum() for r in range(world)])
+        assert per.sum() == pytest.approx(cost.sum())
+        assert per.max() <= cost.sum() / world + 2 * cost.max() + 1e-9
+
+    check()
