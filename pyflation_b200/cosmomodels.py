@@ -149,6 +149,13 @@ class CosmologicalModel(object):
         if getattr(self, "bgmodel", None) is not None:
             data["bg_tresult"] = self.bgmodel.tresult
             data["bg_yresult"] = self.bgmodel.yresult
+        for name in ("potential_func", "nfields", "tend", "tstep_wanted", "simtstart", "cq"):
+            if getattr(self, name, None) is not None:
+                data["param_" + name] = np.asarray(getattr(self, name))
+        if getattr(self, "pot_params", None):
+            data["pot_param_keys"] = np.array(sorted(self.pot_params.keys()))
+            data["pot_param_vals"] = np.array([float(self.pot_params[q]) for q in sorted(self.pot_params.keys())])
+        data["classname"] = np.asarray(self.__class__.__name__)
         np.savez(filename, **data)
         return filename
 
@@ -572,3 +579,47 @@ class FOSuppressOneField(FOCanonicalTwoStage):
                             -arootk * osc * (1 + (self.k / (astar * Hstar)) * 1j),
                             skip=self.suppress_ix)
         return foystart
+
+
+def make_wrapper_model(modelfile, *args, **kwargs):
+    """Return a model instance holding the results stored in ``modelfile`` (the counterpart of
+    ``saveallresults``; the reference's version reads its HDF5 files, cosmomodels.py:1552-1677,
+    this one reads the ``.npz`` archives written here)."""
+    import os
+    if not os.path.isfile(modelfile):
+        raise IOError("File does not exist!")
+    z = np.load(modelfile, allow_pickle=False)
+    classname = str(z["classname"]) if "classname" in z.files else "FOCanonicalTwoStage"
+    cls = globals().get(classname, FOCanonicalTwoStage)
+    pot_params = {}
+    if "pot_param_keys" in z.files:
+        for key, val in zip(z["pot_param_keys"], z["pot_param_vals"]):
+            pot_params[str(key)] = int(val) if str(key) == "nfields" else float(val)
+    nfields = int(z["param_nfields"]) if "param_nfields" in z.files else 1
+    init = dict(potential_func=str(z["param_potential_func"]) if "param_potential_func" in z.files else None,
+                pot_params=pot_params, nfields=nfields)
+    if issubclass(cls, MultiStageDriver):
+        init["k"] = z["k"] if "k" in z.files else None
+        if "bgystart" in z.files:
+            init["bgystart"] = z["bgystart"]
+        if "param_cq" in z.files:
+            init["cq"] = float(z["param_cq"])
+    elif "ystart" in z.files:
+        init["ystart"] = z["ystart"]
+        if issubclass(cls, CanonicalFirstOrder) and "k" in z.files:
+            init["k"] = z["k"]
+    for name in ("tend", "tstep_wanted"):
+        if "param_" + name in z.files:
+            init[name] = float(z["param_" + name])
+    init.update(kwargs)
+    m = cls(*args, **init)
+    m.yresult, m.tresult = z["yresult"], z["tresult"]
+    for name in ("foystart", "fotstart", "fotstartindex", "ainit"):
+        if name in z.files:
+            setattr(m, name, z[name])
+    if "bg_yresult" in z.files and issubclass(cls, MultiStageDriver):
+        bg = m.bgclass(ystart=np.array(z["bg_yresult"][0, :, 0]), tend=m.tend, tstep_wanted=m.tstep_wanted,
+                       potential_func=m.potential_func, pot_params=m.pot_params, nfields=m.nfields)
+        bg.yresult, bg.tresult = z["bg_yresult"], z["bg_tresult"]
+        m.bgmodel = bg
+    return m

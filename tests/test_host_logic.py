@@ -247,3 +247,22 @@ def test_partition_property():
         assert per.max() <= cost.sum() / world + 2 * cost.max() + 1e-9
 
     check()
+
+
+def test_save_and_wrapper_model_roundtrip(tmp_path):
+    """saveallresults -> make_wrapper_model (npz counterpart of cosmomodels.py:236-402, 1552-1677),
+    with results injected the way the reference's tests do."""
+    from pyflation_b200 import cosmomodels as c
+    g = load_fo("c3_hybridquadratic_2p20")
+    m = c.FOCanonicalTwoStage(k=g["k"], nfields=2, potential_func="hybridquadratic",
+                              pot_params={"nfields": 2}, bgystart=g["bgystart"].copy(), cq=50)
+    m.yresult, m.tresult = g["yrows"], g["tresult"][g["rows"]]
+    m.foystart, m.fotstartindex, m.fotstart, m.ainit = g["foystart"], g["fotstartindex"], g["fotstart"], g["ainit"]
+    path = m.saveallresults(filename=str(tmp_path / "run.npz"))
+    w = c.make_wrapper_model(path)
+    assert isinstance(w, c.FOCanonicalTwoStage) and w.nfields == 2 and w.potential_func == "hybridquadratic"
+    assert np.array_equal(w.k, g["k"]) and np.array_equal(w.fotstartindex, g["fotstartindex"])
+    assert np.array_equal(w.yresult.view(np.float64), m.yresult.view(np.float64), equal_nan=True)
+    assert rel_err(w.Pr[-1:], g["Pr_last"]) < 1e-12
+    with pytest.raises(IOError):
+        c.make_wrapper_model(str(tmp_path / "missing.npz"))
