@@ -70,6 +70,42 @@ __device__ __forceinline__ void rk4_mode(const Coef& c, double kval, double h, d
 // Consumer: integrates the modes of logical CTA `cta` (nthreads threads, one mode each; two
 // modes per thread were measured 1.8x slower: the kernel needs its >= 14 warps per SM).
 // `progress` (may be null) is the producer's published record count in fused launches.
+// Time lock-step of the consumer CTAs (full-trajectory launches whose grid is one co-resident
+// wave).  yresult[t] is 5 contiguous rows: while all CTAs work on the same few time steps the
+// union of their stores is a linear sweep through memory and DRAM pages are written once,
+// completely.  CTAs drift apart mainly in the NaN regime, whose length depends on the CTA's
+// k range (its rows are pure stores and run faster than integrated rows); once every mode has
+// started all CTAs do identical work per row and stay aligned by themselves.  A barrier every
+// 512 rows re-aligns them: measured 6.72 -> 6.21 ms per solve together with the record prefetch
+// (periods from 256 to 2048 rows are equivalent, 64 and less cost more than they gain;
+// scripts/pattern_probe6.cu shows the effect on the bare store pattern: 5.8 -> 6.8 TB/s).
+// The barrier is a monotonically increasing arrival counter in global memory: thread 0 adds 1
+// and waits until all consumers of this epoch have arrived.
+constexpr int FO1_LOCKSTEP_ROWS = 512;
+
+struct LockStep {
+    int* counter;                                     // null: no lock-step
+    int nconsumers;
+    int rows;                                         // barrier period
+};
+
+__device__ __forceinline__ void lockstep_barrier(const LockStep& ls, int64_t row) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int target = (int)((row / ls.rows) + 1) * ls.nconsumers;
+        asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ls.counter) : "memory");
+        int have;
+        unsigned spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(have) : "l"(ls.counter) : "memory");
+            if (have >= target) break;
+            __nanosleep(64);
+            if (++spins > (1u << 27)) __trap();
+        }
+    }
+    __syncthreads();
+}
+
 struct Fo1Smem {                                      // one per CTA, owned by the kernel
     alignas(128) double srec[2][FO1_CH * FO1_REC];
     alignas(8) uint64_t bars[2];
@@ -78,7 +114,8 @@ struct Fo1Smem {                                      // one per CTA, owned by t
 
 template <bool PERT>
 __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nthreads,
-                                            const long long* progress, Fo1Smem& sm) {
+                                            const long long* progress, Fo1Smem& sm,
+                                            const LockStep ls = LockStep{nullptr, 0, FO1_LOCKSTEP_ROWS}) {
     constexpr int NV = PERT ? 2 : 5;                  // rows per time step in the output
     constexpr int XO = PERT ? 0 : 3;                  // row of dphi within a time step
     double (&srec)[2][FO1_CH * FO1_REC] = sm.srec;
@@ -127,12 +164,24 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
     const int64_t every = a.out_every;
     int64_t next_out = (a.yout != nullptr && every > 0) ? a.t0 : INT64_MAX;
     const int64_t nan_end = tsmin < a.t1 ? tsmin : a.t1;
-    for (; next_out < nan_end; next_out += every) {
-        if (live) {
+    if (ls.counter) {
+        for (int64_t r = a.t0; r < nan_end; ++r) {            // every == 1 in lock-step launches
+            if (live) {
 #pragma unroll
-            for (int var = 0; var < NV; ++var) __stcs(prow + var * nk, nan2);
+                for (int var = 0; var < NV; ++var) __stcs(prow + var * nk, nan2);
+            }
+            prow += rstride;
+            if ((r - a.t0) % ls.rows == ls.rows - 1) lockstep_barrier(ls, r - a.t0);
         }
-        prow += rstride;
+        next_out = nan_end;
+    } else {
+        for (; next_out < nan_end; next_out += every) {
+            if (live) {
+#pragma unroll
+                for (int var = 0; var < NV; ++var) __stcs(prow + var * nk, nan2);
+            }
+            prow += rstride;
+        }
     }
     int64_t n = nan_end;
     if (n >= a.t1) return;
@@ -159,9 +208,13 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
         mbar_wait(&bars[buf], (uint32_t)((c >> 1) & 1));
         const int64_t base = c0 + c * FO1_CH;
         const int cnt = (int)((a.t1 - base) < FO1_CH ? (a.t1 - base) : FO1_CH);
+        // the record of step q+1 is fetched while step q computes (one step of software
+        // prefetch: shared loads queue behind the back-pressured stores in the LSU)
+        Coef nxt = load_record(&srec[buf][0]);
         for (int q = 0; q < cnt; ++q) {
             n = base + q;
-            const Coef cf = load_record(&srec[buf][q * FO1_REC]);
+            const Coef cf = nxt;
+            if (q + 1 < cnt) nxt = load_record(&srec[buf][(q + 1) * FO1_REC]);
             const bool out = (n == next_out);
             if (n > tsmax) {
                 // ---- regime 3: every mode of the CTA is running
@@ -214,6 +267,8 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
                 prow += rstride;
                 next_out += every;
             }
+            if (ls.counter && (n - a.t0) % ls.rows == ls.rows - 1)
+                lockstep_barrier(ls, n - a.t0);
         }
         __syncthreads();                              // everyone is done reading srec[buf]
         if (tid == 0 && c + 2 < nchunks) issue(c + 2);
@@ -346,7 +401,7 @@ __device__ __forceinline__ void fo1_produce(const FoArgs& a, const ProdArgs& f) 
 }
 
 template <int POT>
-__global__ void __launch_bounds__(512) fo1_fused_kernel(FoArgs a, ProdArgs f, int cthreads) {
+__global__ void __launch_bounds__(512) fo1_fused_kernel(FoArgs a, ProdArgs f, int cthreads, int lockstep) {
     __shared__ int s_cta;
     if (threadIdx.x == 0) s_cta = atomicAdd(f.ws, 1);   // ticket: the first CTA to run produces
     __syncthreads();
@@ -357,8 +412,9 @@ __global__ void __launch_bounds__(512) fo1_fused_kernel(FoArgs a, ProdArgs f, in
     }
     const long long* progress = reinterpret_cast<const long long*>(f.ws + 2);
     __shared__ Fo1Smem sm;
-    if (a.layout == PF_LAYOUT_PERT) fo1_consume<true>(a, cta - 1, cthreads, progress, sm);
-    else fo1_consume<false>(a, cta - 1, cthreads, progress, sm);
+    const LockStep ls{lockstep ? f.ws + 4 : nullptr, (int)gridDim.x - 1, lockstep > 1 ? lockstep : FO1_LOCKSTEP_ROWS};
+    if (a.layout == PF_LAYOUT_PERT) fo1_consume<true>(a, cta - 1, cthreads, progress, sm, ls);
+    else fo1_consume<false>(a, cta - 1, cthreads, progress, sm, ls);
 }
 
 // Grid shape: a whole number c of CTAs per SM, c the smallest for which a CTA holds at most
@@ -414,8 +470,25 @@ bool launch_fo1_fused(const pf_model* m, const FoArgs& a, double simtstart, int6
     const int64_t cthreads = fo1_block(a.nk, sm_count() - 1, a.out_every);   // one SM hosts the producer
     const int64_t block = cthreads > PROD_THREADS ? cthreads : PROD_THREADS;
     const int64_t grid = (a.nk + cthreads - 1) / cthreads + 1;
-#define PF_CALL(POT, NF) \
-    fo1_fused_kernel<POT><<<(unsigned)grid, (unsigned)block, 0, st>>>(a, f, (int)cthreads)
+    // Lock-step needs every CTA resident at once: ask for a cooperative launch (it is refused when
+    // the grid does not fit in one wave) and only then switch the barrier on.
+    static const bool no_lockstep = getenv("PF_FO1_NOLOCKSTEP") != nullptr;
+    const bool want_lockstep = a.out_every == 1 && grid <= sm_count() && !no_lockstep;
+#define PF_CALL(POT, NF)                                                                          \
+    do {                                                                                          \
+        int ct = (int)cthreads, on = 1;                                                           \
+        FoArgs aa = a;                                                                            \
+        ProdArgs ff = f;                                                                          \
+        void* args[] = {&aa, &ff, &ct, &on};                                                      \
+        cudaError_t e = want_lockstep                                                             \
+            ? cudaLaunchCooperativeKernel((void*)fo1_fused_kernel<POT>, dim3((unsigned)grid),     \
+                                          dim3((unsigned)block), args, 0, st)                     \
+            : cudaErrorCooperativeLaunchTooLarge;                                                 \
+        if (e != cudaSuccess) {                                                                   \
+            (void)cudaGetLastError();                                                             \
+            fo1_fused_kernel<POT><<<(unsigned)grid, (unsigned)block, 0, st>>>(a, f, (int)cthreads, 0); \
+        }                                                                                         \
+    } while (0)
     switch (m->potential_id) {
         case PF_MSQPHISQ: PF_CALL(PF_MSQPHISQ, 1); break;
         case PF_LAMBDAPHI4: PF_CALL(PF_LAMBDAPHI4, 1); break;
