@@ -430,18 +430,25 @@ static int sm_count() {
     return sms;
 }
 
-// Full-trajectory launches are bound by the DRAM write pattern and want the largest contiguous
-// segment per CTA (512 threads = 8 KB per row); strided / state-only launches are bound by the
-// fp64 pipe and run ~10 % faster with 128-thread CTAs (measured, scripts/dev_probe.py c5).
+// CTA size.  Full-trajectory launches are bound by the DRAM write pattern: 512-thread CTAs make
+// every row segment of a CTA an aligned 8 KB block (measured with lock-step on three different
+// B200s: 5.78-5.93 ms vs 6.21-6.26 ms for the balanced 448-thread grid), so they are used
+// whenever that grid still fits one wave; otherwise a whole number of equally sized CTAs per SM.
+// Strided / state-only launches are bound by the fp64 pipe and run ~10 % faster with 128-thread
+// CTAs (scripts/dev_probe.py c5).
 static int64_t fo1_block(int64_t nk, int sms, int64_t out_every) {
     int max_threads = out_every == 1 ? 512 : 128;
     if (const char* e = getenv("PF_FO1_MAXT")) max_threads = atoi(e);
     if (max_threads < 32 || max_threads > 512) max_threads = 512;
     int64_t block = 0;
-    for (int64_t per_sm = 1;; ++per_sm) {
-        block = (nk + sms * per_sm - 1) / (sms * per_sm);
-        block = (block + 31) / 32 * 32;
-        if (block <= max_threads) break;
+    if (out_every == 1 && max_threads == 512 && nk >= 16384 && (nk + 511) / 512 <= sms) {
+        block = 512;
+    } else {
+        for (int64_t per_sm = 1;; ++per_sm) {
+            block = (nk + sms * per_sm - 1) / (sms * per_sm);
+            block = (block + 31) / 32 * 32;
+            if (block <= max_threads) break;
+        }
     }
     if (const char* e = getenv("PF_FO1_BLOCK")) block = atoi(e);
     return block;
@@ -473,7 +480,7 @@ bool launch_fo1_fused(const pf_model* m, const FoArgs& a, double simtstart, int6
     // Lock-step needs every CTA resident at once: ask for a cooperative launch (it is refused when
     // the grid does not fit in one wave) and only then switch the barrier on.
     static const bool no_lockstep = getenv("PF_FO1_NOLOCKSTEP") != nullptr;
-    const bool want_lockstep = a.out_every == 1 && grid <= sm_count() && !no_lockstep;
+    const bool want_lockstep = a.out_every == 1 && grid <= 8 * (int64_t)sm_count() && !no_lockstep;
 #define PF_CALL(POT, NF)                                                                          \
     do {                                                                                          \
         int ct = (int)cthreads, on = 1;                                                           \
