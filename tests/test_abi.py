@@ -93,3 +93,44 @@ def test_argument_errors_without_gpu():
         engine.make_model("nflation", {}, 2)                                          # cmpotentials.py:828
     with pytest.raises(ValueError):
         engine.make_model("hybridquadratic", {}, 1)
+
+
+@pytest.mark.parametrize("nf,pert_nan", [(1, 0), (1, 1), (2, 1), (3, 0)])
+def test_host_fill_background_on_cpu(nf, pert_nan):
+    """pf_host_fill_background is host code: checked here without a GPU against a NumPy
+    construction (unsorted start rows, odd sizes, several thread counts)."""
+    from pyflation_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.RandomState(3 + nf)
+    T, nk = 37, 53
+    nb, nvar = 2 * nf + 1, 2 * nf * nf + 2 * nf + 1
+    rec_len, bg_off = int(L.pf_rec_doubles(nf)), 4 * (2 + nf * nf)
+    rec = rng.standard_normal((T, rec_len))
+    tsix = rng.randint(0, T + 5, nk).astype(np.int64)          # some modes never start
+    ystart = rng.standard_normal((nvar, nk)) + 1j * rng.standard_normal((nvar, nk))
+    want = np.full((T, nvar, nk), 7.0 + 7.0j)
+    for t in range(T):
+        for k in range(nk):
+            if t < tsix[k]:
+                want[t, :nb if not pert_nan else nvar, k] = np.nan + 1j * np.nan
+            elif t == tsix[k]:
+                want[t, :nb, k] = ystart[:nb, k]
+            else:
+                want[t, :nb, k] = rec[t, bg_off:bg_off + nb]
+    for nthreads in (1, 3, 64):
+        out = np.full((T, nvar, nk), 7.0 + 7.0j)
+        rc = L.pf_host_fill_background(ctypes.c_void_p(out.ctypes.data), nf, nk, 0, T,
+                                       ctypes.c_void_p(rec.ctypes.data), rec_len, bg_off,
+                                       ctypes.c_void_p(tsix.ctypes.data), ctypes.c_void_p(ystart.ctypes.data),
+                                       pert_nan, nthreads)
+        assert rc == 0
+        assert np.array_equal(out.view(np.float64), want.view(np.float64), equal_nan=True)
+    # a sub-range of rows leaves the others untouched
+    out = np.full((T, nvar, nk), 7.0 + 7.0j)
+    assert L.pf_host_fill_background(ctypes.c_void_p(out.ctypes.data), nf, nk, 10, 20,
+                                     ctypes.c_void_p(rec.ctypes.data), rec_len, bg_off,
+                                     ctypes.c_void_p(tsix.ctypes.data), ctypes.c_void_p(ystart.ctypes.data),
+                                     pert_nan, 2) == 0
+    assert np.all(out[:10] == 7.0 + 7.0j) and np.all(out[20:] == 7.0 + 7.0j)
+    assert np.array_equal(out[10:20].view(np.float64), want[10:20].view(np.float64), equal_nan=True)
+    assert L.pf_host_fill_background(None, nf, nk, 0, T, None, rec_len, bg_off, None, None, 0, 1) == -1
