@@ -266,3 +266,22 @@ def test_save_and_wrapper_model_roundtrip(tmp_path):
     assert rel_err(w.Pr[-1:], g["Pr_last"]) < 1e-12
     with pytest.raises(IOError):
         c.make_wrapper_model(str(tmp_path / "missing.npz"))
+
+
+def test_committed_bench_record_has_contract_keys():
+    """The bench line recorded for this round carries every key of the measurement contract."""
+    import json
+    from conftest import ROOT
+    line = json.loads(open(os.path.join(ROOT, "profiles", "r1_bench_n1.json")).read())
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches",
+                "roofline", "cpu_baseline"):
+        assert key in line, key
+    assert line["dtype"] == "f64" and line["scaling"] == "weak" and line["vs_baseline"] is None
+    assert "workload" in line["config"] and "model" not in line["config"]
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
+    assert abs(line["roofline"]["frac"] - line["roofline"]["achieved"] / line["roofline"]["peak"]) < 1e-12
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(line["cpu_baseline"])
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"])
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(line["clocks"])
+    assert line["gpu_launches"] == line["steps"] and line["e2e"]["value"] < line["value"]
