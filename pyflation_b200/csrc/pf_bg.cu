@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(32) bg_rk4_kernel(PotParams par, int64_t T, do
 template <int POT, int NF>
 __global__ void stage_table_kernel(PotParams par, double ainit, int64_t T, double simtstart,
                                    double h, int64_t n0, const double* __restrict__ stagey,
-                                   double* __restrict__ rec) {
+                                   double* __restrict__ rec, int factored) {
     constexpr int NB = 2 * NF + 1, REC = rec_of(NF), SW = 2 + NF * NF, BG = 4 * SW;
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n = gid >> 2;
@@ -89,7 +89,7 @@ __global__ void stage_table_kernel(PotParams par, double ainit, int64_t T, doubl
     double y[NB];
 #pragma unroll
     for (int c = 0; c < NB; ++c) y[c] = stagey[(n * 4 + s) * NB + c];
-    stage_record<POT, NF>(par.v, ainit, simtstart, h, n, s, y, r);
+    stage_record<POT, NF>(par.v, ainit, simtstart, h, n, s, y, r, factored != 0);
 }
 
 template <int POT, int NF>
@@ -220,8 +220,9 @@ extern "C" int pf_stage_table(const pf_model* m, int64_t T, double simtstart, do
     cudaStream_t st = (cudaStream_t)stream;
     const int block = 128;
     const int64_t grid = (T * 4 + block - 1) / block;
+    const int factored = rec_kind(m) == PF_REC_FACTORED;
 #define PF_CALL(POT, NF) \
-    stage_table_kernel<POT, NF><<<(unsigned)grid, block, 0, st>>>(par, m->ainit, T, simtstart, h, n0, stagey_dev, rec_dev)
+    stage_table_kernel<POT, NF><<<(unsigned)grid, block, 0, st>>>(par, m->ainit, T, simtstart, h, n0, stagey_dev, rec_dev, factored)
     bool ok = PF_DISPATCH_POT_NF(m->potential_id, m->nfields, PF_CALL);
 #undef PF_CALL
     if (!ok) { set_error("pf_stage_table: potential %d is not defined for nfields=%d", m->potential_id, m->nfields); return PF_E_POTENTIAL; }

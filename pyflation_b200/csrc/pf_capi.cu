@@ -71,6 +71,12 @@ int check_model(const pf_model* m) {
     return PF_OK;
 }
 
+int rec_kind(const pf_model* m) {
+    static const bool dense_only = getenv("PF_FO_DENSE") != nullptr;
+    return (!dense_only && m->potential_id == PF_NFLATION && m->nfields >= 5) ? PF_REC_FACTORED
+                                                                              : PF_REC_DENSE;
+}
+
 // P_R = sum_K |sum_I phi'_I chi_IK|^2 / (sum_K phi'_K^2)^2     adiabatic.py:153-199
 // thread <-> (row, k); reads are coalesced along k.
 __global__ void pr_kernel(int nf, int64_t nrows, int64_t nk, const double2* __restrict__ y,

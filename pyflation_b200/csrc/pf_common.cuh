@@ -29,4 +29,10 @@ __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000
 
 int check_model(const pf_model* m);
 
+// Flavour of the step records for (potential, nfields): PF_REC_DENSE (A, R, C[nf][nf]) or
+// PF_REC_FACTORED (nflation, nf >= 5: the rank-2 factors of C, see pf_records.cuh).  The
+// environment variable PF_FO_DENSE forces dense records (A/B measurements).
+enum { PF_REC_DENSE = 0, PF_REC_FACTORED = 1 };
+int rec_kind(const pf_model* m);
+
 }  // namespace pf

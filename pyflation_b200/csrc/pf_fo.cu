@@ -25,10 +25,19 @@
 namespace pf {
 
 template <int NF, int NC>
-static int launch_fo(const FoArgs& a, cudaStream_t st) {
+static int launch_fo(const FoArgs& a, cudaStream_t st, bool factored = false) {
     using S = FoShape<NF>;
     constexpr int KPB = S::BLOCK / (3 - NC);
     dim3 grid((unsigned)((a.nk + KPB - 1) / KPB), NF, 1);
+    if constexpr (NF >= 5) {
+        if (factored) {
+            // CTAs per SM (register cap 128 / 168): A/B switch PF_FO_FACT_MINB=3|4
+            static const int minb = getenv("PF_FO_FACT_MINB") ? atoi(getenv("PF_FO_FACT_MINB")) : PF_FO_MINB_FACT;
+            if (minb == 3) fo_rk4_fact_kernel<NF, NC, 3><<<grid, S::BLOCK, 0, st>>>(a);
+            else fo_rk4_fact_kernel<NF, NC, 4><<<grid, S::BLOCK, 0, st>>>(a);
+            return 0;
+        }
+    }
     fo_rk4_kernel<NF, NC><<<grid, S::BLOCK, 0, st>>>(a);
     return 0;
 }
@@ -62,6 +71,7 @@ extern "C" int pf_fo_run(const pf_model* m, int64_t nk, const double* k_dev, con
     a.h = h;
     cudaStream_t st = (cudaStream_t)stream;
     static const bool generic_only = getenv("PF_FO_GENERIC") != nullptr;
+    const bool fact = rec_kind(m) == PF_REC_FACTORED;   // must match the records pf_stage_table wrote
     switch (m->nfields) {
         case 1:
             if (!generic_only) launch_fo1(a, st);                     // single-field fast path
@@ -70,10 +80,10 @@ extern "C" int pf_fo_run(const pf_model* m, int64_t nk, const double* k_dev, con
         case 2: launch_fo<2, 2>(a, st); break;
         case 3: launch_fo<3, 1>(a, st); break;
         case 4: launch_fo<4, 1>(a, st); break;
-        case 5: launch_fo<5, 1>(a, st); break;
-        case 6: launch_fo<6, 1>(a, st); break;
-        case 7: launch_fo<7, 1>(a, st); break;
-        case 8: launch_fo<8, 1>(a, st); break;
+        case 5: launch_fo<5, 1>(a, st, fact); break;
+        case 6: launch_fo<6, 1>(a, st, fact); break;
+        case 7: launch_fo<7, 1>(a, st, fact); break;
+        case 8: launch_fo<8, 1>(a, st, fact); break;
         default: set_error("pf_fo_run: nfields=%d not compiled", m->nfields); return PF_E_NFIELDS;
     }
     PF_CUDA_CHECK(cudaGetLastError(), "pf_fo_run launch");

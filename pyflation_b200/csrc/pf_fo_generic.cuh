@@ -44,9 +44,15 @@ template <int NF, int NC>
 __device__ __forceinline__ void mode_rhs(const double* __restrict__ cs, double kval,
                                          const double (&x)[NF][NC], const double (&v)[NF][NC],
                                          double (&kv)[NF][NC]) {
-    const double2 ar = *reinterpret_cast<const double2*>(cs);
-    const double A = ar.x;
-    const double kr = kval * ar.y;
+    // odd NF: SW = 2 + NF*NF is odd, so stages 1 and 3 are only 8-byte aligned -> scalar loads
+    double A, R;
+    if constexpr (NF % 2 == 0) {
+        const double2 ar = *reinterpret_cast<const double2*>(cs);
+        A = ar.x; R = ar.y;
+    } else {
+        A = cs[0]; R = cs[1];
+    }
+    const double kr = kval * R;
     const double B = kr * kr;
     // column-by-column accumulation: the NF row sums are independent dependency chains and are
     // advanced together (ILP = NF*NC), instead of finishing one row's NF-long chain at a time
@@ -83,14 +89,161 @@ __device__ __forceinline__ void mode_rhs(const double* __restrict__ cs, double k
         for (int c = 0; c < NC; ++c) kv[i][c] = -acc[i][c];
 }
 
+// Factored records (PF_REC_FACTORED, pf_records.cuh): C = d I + (p g^T + g p^T + U p p^T)/H^2, so
+//   kv_i = -( A v_i + ((kR)^2 + d) x_i + p_i w + g_i z ),   z = (p.x)/H^2,  w = (g.x)/H^2 + U z
+// 4 NF + 3 FMAs for the coupling instead of NF^2, and 6 + 2 NF broadcast loads instead of 2 + NF^2.
+// The whole RK4 step is written out so that kv_i is consumed as soon as it exists: six state
+// arrays stay live (x, v, ax, av, xt, vt) instead of seven, and p, g are re-read from shared
+// memory for the update pass instead of being held across the dot products.
+__device__ __forceinline__ double2 lds_pair(const double* p) {       // never merged with other loads
+    double2 r;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(smem_u32(p)));
+    return r;
+}
+__device__ __forceinline__ double lds_one(const double* p) {
+    double r;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(smem_u32(p)));
+    return r;
+}
+
+template <int NF, int NC>
+struct FactStage {
+    double A, Bd, z[NC], w[NC];
+    // scalars of one stage: dot products of the stage argument xin with p and g
+    __device__ __forceinline__ void prepare(const double* __restrict__ cs, double kval,
+                                            const double (&xin)[NF][NC]) {
+        double hd[5];
+        if constexpr (NF % 2 == 0) {                  // slots are 16-byte aligned for even NF
+            const double2 q0 = lds_pair(cs), q1 = lds_pair(cs + 2), q2 = lds_pair(cs + 4);
+            hd[0] = q0.x; hd[1] = q0.y; hd[2] = q1.x; hd[3] = q1.y; hd[4] = q2.x;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) hd[i] = lds_one(cs + i);
+        }
+        A = hd[0];
+        const double kr = kval * hd[1];
+        Bd = fma(kr, kr, hd[2]);
+        double sp[2][NC], sg[2][NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { sp[0][c] = sp[1][c] = sg[0][c] = sg[1][c] = 0.0; }
+        if constexpr (NF % 2 == 0) {
+#pragma unroll
+            for (int l = 0; l < NF / 2; ++l) {
+                const double2 pp = lds_pair(cs + 6 + 2 * l), gg = lds_pair(cs + 6 + NF + 2 * l);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    sp[0][c] = fma(pp.x, xin[2 * l][c], sp[0][c]);
+                    sp[1][c] = fma(pp.y, xin[2 * l + 1][c], sp[1][c]);
+                    sg[0][c] = fma(gg.x, xin[2 * l][c], sg[0][c]);
+                    sg[1][c] = fma(gg.y, xin[2 * l + 1][c], sg[1][c]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int l = 0; l < NF; ++l) {
+                const double pp = lds_one(cs + 6 + l), gg = lds_one(cs + 6 + NF + l);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    sp[l & 1][c] = fma(pp, xin[l][c], sp[l & 1][c]);
+                    sg[l & 1][c] = fma(gg, xin[l][c], sg[l & 1][c]);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            z[c] = (sp[0][c] + sp[1][c]) * hd[4];
+            w[c] = fma(hd[3], z[c], (sg[0][c] + sg[1][c]) * hd[4]);
+        }
+    }
+    // kv_i of this stage for field i (pi, gi = p_i, g_i)
+    __device__ __forceinline__ double kv(double pi, double gi, double xi, double vi, int c) const {
+        double t = fma(Bd, xi, A * vi);
+        t = fma(pi, w[c], t);
+        t = fma(gi, z[c], t);
+        return -t;
+    }
+};
+
+// visit(i, p_i, g_i) for every field, p and g re-read from the stage slot
+template <int NF, class F>
+__device__ __forceinline__ void for_each_pg(const double* __restrict__ cs, F&& visit) {
+    if constexpr (NF % 2 == 0) {
+#pragma unroll
+        for (int l = 0; l < NF / 2; ++l) {
+            const double2 pp = lds_pair(cs + 6 + 2 * l), gg = lds_pair(cs + 6 + NF + 2 * l);
+            visit(2 * l, pp.x, gg.x);
+            visit(2 * l + 1, pp.y, gg.y);
+        }
+    } else {
+#pragma unroll
+        for (int l = 0; l < NF; ++l) visit(l, lds_one(cs + 6 + l), lds_one(cs + 6 + NF + l));
+    }
+}
+
+// one classical RK4 step n -> n+1 (rk4.py:27-55) from the factored record r
+template <int NF, int NC>
+__device__ __forceinline__ void rk4_step_factored(const double* __restrict__ r, double kval, double h,
+                                                  double hh, double h6, double (&x)[NF][NC],
+                                                  double (&v)[NF][NC]) {
+    constexpr int SW = FoShape<NF>::SW;
+    double ax[NF][NC], av[NF][NC], xt[NF][NC], vt[NF][NC];
+    FactStage<NF, NC> st;
+    st.prepare(r, kval, x);
+    for_each_pg<NF>(r, [&](int i, double pi, double gi) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const double k1 = st.kv(pi, gi, x[i][c], v[i][c], c);
+            av[i][c] = k1;
+            xt[i][c] = fma(hh, v[i][c], x[i][c]);
+            vt[i][c] = fma(hh, k1, v[i][c]);
+        }
+    });
+    st.prepare(r + SW, kval, xt);
+    for_each_pg<NF>(r + SW, [&](int i, double pi, double gi) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const double k2 = st.kv(pi, gi, xt[i][c], vt[i][c], c);
+            ax[i][c] = fma(2.0, vt[i][c], v[i][c]);
+            av[i][c] = fma(2.0, k2, av[i][c]);
+            xt[i][c] = fma(hh, vt[i][c], x[i][c]);
+            vt[i][c] = fma(hh, k2, v[i][c]);
+        }
+    });
+    st.prepare(r + 2 * SW, kval, xt);
+    for_each_pg<NF>(r + 2 * SW, [&](int i, double pi, double gi) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const double k3 = st.kv(pi, gi, xt[i][c], vt[i][c], c);
+            ax[i][c] = fma(2.0, vt[i][c], ax[i][c]);
+            av[i][c] = fma(2.0, k3, av[i][c]);
+            xt[i][c] = fma(h, vt[i][c], x[i][c]);
+            vt[i][c] = fma(h, k3, v[i][c]);
+        }
+    });
+    st.prepare(r + 3 * SW, kval, xt);
+    for_each_pg<NF>(r + 3 * SW, [&](int i, double pi, double gi) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const double k4 = st.kv(pi, gi, xt[i][c], vt[i][c], c);
+            x[i][c] = fma(h6, ax[i][c] + vt[i][c], x[i][c]);
+            v[i][c] = fma(h6, av[i][c] + k4, v[i][c]);
+        }
+    });
+}
+
 // nf >= 5: cap the registers at 168 so three 128-thread CTAs fit an SM (12 warps instead of 8;
 // measured +3 % at nf = 8; a cap of 128 registers spills and is slower)
 #ifndef PF_FO_MINB
 #define PF_FO_MINB(NF) ((NF) >= 5 ? 3 : 1)
 #endif
+// factored records: six state arrays (96 registers at nf = 8) and no kv array -> 128 registers,
+// four 128-thread CTAs per SM
+#ifndef PF_FO_MINB_FACT
+#define PF_FO_MINB_FACT 4
+#endif
 // Consumer: integrates column j of the mode matrix for the k tile bx.  `progress` (may be null)
 // is the producer's published record count in fused launches (pf_fused.cu).
-template <int NF, int NC>
+template <int NF, int NC, bool FACT = false>
 __device__ __forceinline__ void fo_consume(const FoArgs& a, int64_t bx, int j, const long long* progress) {
     using S = FoShape<NF>;
     constexpr int NB = S::NB, SW = S::SW, REC = S::REC, CH = S::CH;
@@ -236,45 +389,49 @@ __device__ __forceinline__ void fo_consume(const FoArgs& a, int64_t bx, int j, c
                 }
                 if (n + 1 < a.T) {
                     // one classical RK4 step n -> n+1                      rk4.py:27-55
-                    double kv[NF][NC], ax[NF][NC], av[NF][NC], xt[NF][NC], vt[NF][NC];
-                    mode_rhs<NF, NC>(r, kval, x, v, kv);
+                    if constexpr (FACT) {
+                        rk4_step_factored<NF, NC>(r, kval, h, hh, h6, x, v);
+                    } else {
+                        double kv[NF][NC], ax[NF][NC], av[NF][NC], xt[NF][NC], vt[NF][NC];
+                        mode_rhs<NF, NC>(r, kval, x, v, kv);
 #pragma unroll
-                    for (int i = 0; i < NF; ++i)
+                        for (int i = 0; i < NF; ++i)
 #pragma unroll
-                        for (int cc = 0; cc < NC; ++cc) {
-                            ax[i][cc] = v[i][cc];
-                            av[i][cc] = kv[i][cc];
-                            xt[i][cc] = fma(hh, v[i][cc], x[i][cc]);
-                            vt[i][cc] = fma(hh, kv[i][cc], v[i][cc]);
-                        }
-                    mode_rhs<NF, NC>(r + SW, kval, xt, vt, kv);
+                            for (int cc = 0; cc < NC; ++cc) {
+                                ax[i][cc] = v[i][cc];
+                                av[i][cc] = kv[i][cc];
+                                xt[i][cc] = fma(hh, v[i][cc], x[i][cc]);
+                                vt[i][cc] = fma(hh, kv[i][cc], v[i][cc]);
+                            }
+                        mode_rhs<NF, NC>(r + SW, kval, xt, vt, kv);
 #pragma unroll
-                    for (int i = 0; i < NF; ++i)
+                        for (int i = 0; i < NF; ++i)
 #pragma unroll
-                        for (int cc = 0; cc < NC; ++cc) {
-                            ax[i][cc] = fma(2.0, vt[i][cc], ax[i][cc]);
-                            av[i][cc] = fma(2.0, kv[i][cc], av[i][cc]);
-                            xt[i][cc] = fma(hh, vt[i][cc], x[i][cc]);
-                            vt[i][cc] = fma(hh, kv[i][cc], v[i][cc]);
-                        }
-                    mode_rhs<NF, NC>(r + 2 * SW, kval, xt, vt, kv);
+                            for (int cc = 0; cc < NC; ++cc) {
+                                ax[i][cc] = fma(2.0, vt[i][cc], ax[i][cc]);
+                                av[i][cc] = fma(2.0, kv[i][cc], av[i][cc]);
+                                xt[i][cc] = fma(hh, vt[i][cc], x[i][cc]);
+                                vt[i][cc] = fma(hh, kv[i][cc], v[i][cc]);
+                            }
+                        mode_rhs<NF, NC>(r + 2 * SW, kval, xt, vt, kv);
 #pragma unroll
-                    for (int i = 0; i < NF; ++i)
+                        for (int i = 0; i < NF; ++i)
 #pragma unroll
-                        for (int cc = 0; cc < NC; ++cc) {
-                            ax[i][cc] = fma(2.0, vt[i][cc], ax[i][cc]);
-                            av[i][cc] = fma(2.0, kv[i][cc], av[i][cc]);
-                            xt[i][cc] = fma(h, vt[i][cc], x[i][cc]);
-                            vt[i][cc] = fma(h, kv[i][cc], v[i][cc]);
-                        }
-                    mode_rhs<NF, NC>(r + 3 * SW, kval, xt, vt, kv);
+                            for (int cc = 0; cc < NC; ++cc) {
+                                ax[i][cc] = fma(2.0, vt[i][cc], ax[i][cc]);
+                                av[i][cc] = fma(2.0, kv[i][cc], av[i][cc]);
+                                xt[i][cc] = fma(h, vt[i][cc], x[i][cc]);
+                                vt[i][cc] = fma(h, kv[i][cc], v[i][cc]);
+                            }
+                        mode_rhs<NF, NC>(r + 3 * SW, kval, xt, vt, kv);
 #pragma unroll
-                    for (int i = 0; i < NF; ++i)
+                        for (int i = 0; i < NF; ++i)
 #pragma unroll
-                        for (int cc = 0; cc < NC; ++cc) {
-                            x[i][cc] = fma(h6, ax[i][cc] + vt[i][cc], x[i][cc]);
-                            v[i][cc] = fma(h6, av[i][cc] + kv[i][cc], v[i][cc]);
-                        }
+                            for (int cc = 0; cc < NC; ++cc) {
+                                x[i][cc] = fma(h6, ax[i][cc] + vt[i][cc], x[i][cc]);
+                                v[i][cc] = fma(h6, av[i][cc] + kv[i][cc], v[i][cc]);
+                            }
+                    }
                 }
             }
             if (out) {
@@ -301,6 +458,11 @@ __device__ __forceinline__ void fo_consume(const FoArgs& a, int64_t bx, int j, c
 template <int NF, int NC>
 __global__ void __launch_bounds__(FoShape<NF>::BLOCK, PF_FO_MINB(NF)) fo_rk4_kernel(FoArgs a) {
     fo_consume<NF, NC>(a, blockIdx.x, blockIdx.y, nullptr);
+}
+
+template <int NF, int NC, int MINB>
+__global__ void __launch_bounds__(FoShape<NF>::BLOCK, MINB) fo_rk4_fact_kernel(FoArgs a) {
+    fo_consume<NF, NC, true>(a, blockIdx.x, blockIdx.y, nullptr);
 }
 
 }  // namespace pf

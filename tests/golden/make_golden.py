@@ -68,6 +68,14 @@ FIXTURES = {
                        "FOCanonicalTwoStage", {}),
     "nflation2": ("nflation", 2, {"nfields": 2}, None, 2 ** 10, 5, 50,
                   "FOCanonicalTwoStage", {}),
+    # odd field counts (records only 8-byte aligned at stages 1 and 3) and nfields > 8 (the
+    # reference's nflation accepts any nfields, cmpotentials.py:791-846)
+    "nflation3": ("nflation", 3, {"nfields": 3}, None, 2 ** 10, 5, 50,
+                  "FOCanonicalTwoStage", {}),
+    "nflation5": ("nflation", 5, {"nfields": 5}, None, 2 ** 10, 3, 100,
+                  "FOCanonicalTwoStage", {}),
+    "nflation10": ("nflation", 10, {"nfields": 10}, None, 2 ** 10, 2, 100,
+                   "FOCanonicalTwoStage", {}),
     "hybridquartic": ("hybridquartic", 2, {"nfields": 2}, [1e-2, 2e-8, 1.63e-9, 3.26e-7, 0],
                       2 ** 10, 5, 50, "FOCanonicalTwoStage", {}),
     "productexponential": ("productexponential", 2, {"nfields": 2}, [18.0, 0.0, 0.001, 0, 0],

@@ -34,12 +34,20 @@ def run_model(g):
 RAW_PHASE_EXCEPTIONS = {}
 
 
+# hybridquartic's waterfall instability amplifies a 1-ulp change of the inputs to 6.2e-9 in the
+# reference's own background (conditioning.json); the GPU path measures 8.6e-10 against the
+# golden file and is held to 2e-9.  Every other fixture: the north-star 1e-9.
+WIDENED = {"hybridquartic": 2e-9}
+
+
 def tolerances(name):
-    """(background / phase-free tolerance, amplitude tolerance, raw complex tolerance).
-    1e-9 unless the reference's own computation is ill-conditioned for this fixture
-    (tests/golden/make_conditioning.py: response of the oracle to a 1-ulp input change)."""
+    """(background / phase-free tolerance, amplitude tolerance, raw complex tolerance):
+    1e-9, except the one fixture whose reference computation is itself ill-conditioned beyond
+    that (tests/golden/make_conditioning.py: response of the oracle to a 1-ulp input change)."""
     c = CONDITIONING[name]
-    return (max(TOL, 100 * c["bg"]), max(TOL, 100 * c["amp"]), RAW_PHASE_EXCEPTIONS.get(name, TOL))
+    assert 10 * c["bg"] < TOL or name in WIDENED, "fixture %s needs a stated tolerance" % name
+    tol = WIDENED.get(name, TOL)
+    return (tol, tol, RAW_PHASE_EXCEPTIONS.get(name, tol))
 
 
 def phase_normalised(y, y0, nf):
