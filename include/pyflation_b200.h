@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 1
+#define PF_ABI_VERSION 2
 #define PF_MAX_NFIELDS 8          /* compiled instantiations: nf = 1..8 */
 #define PF_MAX_PARAMS 8
 
@@ -142,11 +142,16 @@ int pf_stage_table(const pf_model *m, int64_t T, double simtstart, double h, int
  *   (read when t0 > tsix_k), overwritten with the state at row t1 (for windowed runs).
  *   yout_dev c128: row (t - t0)/out_every of the window for every t in [t0,t1) with
  *   (t - t0) % out_every == 0, each row [nvar][nk]; out_every = 0 stores no trajectory.
+ *   out_pitch: modes per output row, 0 = nk.  A k-sharded run passes the width of the
+ *   assembled result and yout_dev = &assembled[0][0][k0] (k0 = first column of this slab): the
+ *   kernel then writes its columns straight into the assembled [rows][nvar][out_pitch] array,
+ *   which may live on another GPU of the box (peer memory, see pf_peer_*), i.e. the k-gather
+ *   rides on the kernel's own stores over NVLink instead of a separate collective.
  *   flags_dev: int32, OR-ed with PF_FLAG_* (may be NULL). */
 int pf_fo_run(const pf_model *m, int64_t nk, const double *k_dev, const int64_t *tsix_dev,
               const double *ystart_dev, const double *rec_dev, int64_t T, double h,
               int64_t t0, int64_t t1, double *state_dev, double *yout_dev, int64_t out_every,
-              int32_t layout, int32_t *flags_dev, void *stream);
+              int32_t layout, int64_t out_pitch, int32_t *flags_dev, void *stream);
 
 /* ---- one-call solve of the first window [0, t1): K1 + K1b + K2 ----
  * What rk4.rkdriver_tsix does for a CanonicalFirstOrder model in one call.  For single-field
@@ -163,7 +168,8 @@ int64_t pf_solve_scratch_doubles(int nfields, int64_t T);
 int pf_fo_solve(const pf_model *m, int64_t nk, const double *k_dev, const int64_t *tsix_dev,
                 const double *ystart_dev, int64_t n0, const double *y0_host, int64_t T,
                 double simtstart, double h, int64_t t1, double *scratch_dev, double *state_dev,
-                double *yout_dev, int64_t out_every, int32_t layout, int32_t *ws_dev, void *stream);
+                double *yout_dev, int64_t out_every, int32_t layout, int64_t out_pitch,
+                int32_t *ws_dev, void *stream);
 
 /* ---- K6 / K7: initial-condition glue on the device (FOCanonicalTwoStage.setfoics) ----
  * pf_crossing_rows: rows_dev[k] = first row t with cum_dev[t] > k, cum_dev[T] the running
@@ -209,6 +215,20 @@ int pf_host_fill_background(double *yout_host, int nfields, int64_t nk, int64_t 
  * column offset k0 (the on-GPU permute after an NCCL all-gather of slabs). */
 int pf_scatter_slab(int64_t nrows_times_nvar, int64_t nk_r, int64_t nk, int64_t k0,
                     const double *slab_dev, double *full_dev, void *stream);
+
+/* ---- peer memory: the destination of a fused k-gather (one process per GPU, one box) ----
+ * The rank that assembles a result allocates it with pf_peer_alloc (a dedicated cudaMalloc, so
+ * that the whole allocation can be exported), exports a 64-byte handle (cudaIpcGetMemHandle),
+ * ships it to the other ranks by any means (torch.distributed in pyflation_b200/parallel.py);
+ * they map it with pf_peer_open and pass the mapped pointer (+ their column offset) as yout_dev
+ * with out_pitch = total width.  Stores travel over NVLink / NVSwitch.  The writers must
+ * synchronise their stream and the ranks must meet at a barrier before the owner reads. */
+#define PF_PEER_HANDLE_BYTES 64
+int pf_peer_alloc(size_t bytes, void **ptr_dev);
+int pf_peer_free(void *ptr_dev);
+int pf_peer_export(const void *ptr_dev, unsigned char handle[PF_PEER_HANDLE_BYTES]);
+int pf_peer_open(const unsigned char handle[PF_PEER_HANDLE_BYTES], void **ptr_dev);
+int pf_peer_close(void *ptr_dev);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,7 @@ PF_MAX_NFIELDS = 8
 PF_MAX_PARAMS = 8
 PF_FLAG_BG_MISMATCH = 1
 PF_LAYOUT_FULL, PF_LAYOUT_PERT = 0, 1
+PF_PEER_HANDLE_BYTES = 64
 
 # names every build must export (checked by tests/test_abi.py against the header)
 EXPORTS = [
@@ -23,6 +24,7 @@ EXPORTS = [
     "pf_rec_doubles", "pf_bg_run", "pf_stage_table", "pf_fo_run", "pf_solve_scratch_doubles",
     "pf_fo_solve", "pf_pr_spectrum", "pf_scatter_slab", "pf_copy_rows_d2h",
     "pf_host_fill_background", "pf_crossing_rows", "pf_bunch_davies", "pf_derivs",
+    "pf_peer_alloc", "pf_peer_free", "pf_peer_export", "pf_peer_open", "pf_peer_close",
 ]
 
 
@@ -82,11 +84,11 @@ def lib():
     L.pf_bg_run.argtypes = [mp, c_i64, c_dbl, c_i64, ctypes.POINTER(c_dbl), c_vp, c_vp, c_vp]
     L.pf_stage_table.argtypes = [mp, c_i64, c_dbl, c_dbl, c_i64, c_vp, c_vp, c_vp, c_vp]
     L.pf_fo_run.argtypes = [mp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_dbl, c_i64, c_i64,
-                            c_vp, c_vp, c_i64, ctypes.c_int32, c_vp, c_vp]
+                            c_vp, c_vp, c_i64, ctypes.c_int32, c_i64, c_vp, c_vp]
     L.pf_solve_scratch_doubles.argtypes = [c_int, c_i64]
     L.pf_solve_scratch_doubles.restype = c_i64
     L.pf_fo_solve.argtypes = [mp, c_i64, c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(c_dbl), c_i64, c_dbl,
-                              c_dbl, c_i64, c_vp, c_vp, c_vp, c_i64, ctypes.c_int32, c_vp, c_vp]
+                              c_dbl, c_i64, c_vp, c_vp, c_vp, c_i64, ctypes.c_int32, c_i64, c_vp, c_vp]
     c_sz = ctypes.c_size_t
     L.pf_copy_rows_d2h.argtypes = [c_vp, c_sz, c_vp, c_sz, c_sz, c_sz, c_vp]
     L.pf_host_fill_background.argtypes = [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64,
@@ -97,6 +99,11 @@ def lib():
     L.pf_bunch_davies.argtypes = [c_int, c_i64, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_dbl, c_dbl, c_int,
                                   c_int, c_vp, c_vp]
     L.pf_derivs.argtypes = [mp, c_int, c_i64, c_vp, c_dbl, c_vp, c_vp, c_vp]
+    L.pf_peer_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(c_vp)]
+    L.pf_peer_free.argtypes = [c_vp]
+    L.pf_peer_export.argtypes = [c_vp, ctypes.c_char_p]
+    L.pf_peer_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(c_vp)]
+    L.pf_peer_close.argtypes = [c_vp]
     _lib = L
     return L
 

@@ -176,3 +176,35 @@ extern "C" int pf_scatter_slab(int64_t nrows_times_nvar, int64_t nk_r, int64_t n
                   "pf_scatter_slab");
     return PF_OK;
 }
+
+// ---- peer memory for the fused k-gather (see include/pyflation_b200.h) ----
+extern "C" int pf_peer_alloc(size_t bytes, void** ptr_dev) {
+    if (!ptr_dev || bytes == 0) { set_error("pf_peer_alloc: bad arguments"); return PF_E_ARG; }
+    PF_CUDA_CHECK(cudaMalloc(ptr_dev, bytes), "pf_peer_alloc");
+    return PF_OK;
+}
+extern "C" int pf_peer_free(void* ptr_dev) {
+    if (!ptr_dev) return PF_OK;
+    PF_CUDA_CHECK(cudaFree(ptr_dev), "pf_peer_free");
+    return PF_OK;
+}
+extern "C" int pf_peer_export(const void* ptr_dev, unsigned char handle[PF_PEER_HANDLE_BYTES]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == PF_PEER_HANDLE_BYTES, "handle size");
+    if (!ptr_dev || !handle) { set_error("pf_peer_export: null argument"); return PF_E_ARG; }
+    cudaIpcMemHandle_t h;
+    PF_CUDA_CHECK(cudaIpcGetMemHandle(&h, const_cast<void*>(ptr_dev)), "pf_peer_export");
+    memcpy(handle, &h, sizeof(h));
+    return PF_OK;
+}
+extern "C" int pf_peer_open(const unsigned char handle[PF_PEER_HANDLE_BYTES], void** ptr_dev) {
+    if (!ptr_dev || !handle) { set_error("pf_peer_open: null argument"); return PF_E_ARG; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    PF_CUDA_CHECK(cudaIpcOpenMemHandle(ptr_dev, h, cudaIpcMemLazyEnablePeerAccess), "pf_peer_open");
+    return PF_OK;
+}
+extern "C" int pf_peer_close(void* ptr_dev) {
+    if (!ptr_dev) return PF_OK;
+    PF_CUDA_CHECK(cudaIpcCloseMemHandle(ptr_dev), "pf_peer_close");
+    return PF_OK;
+}

@@ -49,7 +49,8 @@ using namespace pf;
 extern "C" int pf_fo_run(const pf_model* m, int64_t nk, const double* k_dev, const int64_t* tsix_dev,
                          const double* ystart_dev, const double* rec_dev, int64_t T, double h,
                          int64_t t0, int64_t t1, double* state_dev, double* yout_dev,
-                         int64_t out_every, int32_t layout, int32_t* flags_dev, void* stream) {
+                         int64_t out_every, int32_t layout, int64_t out_pitch, int32_t* flags_dev,
+                         void* stream) {
     int rc = check_model(m);
     if (rc) return rc;
     if (nk < 0 || T < 1 || t0 < 0 || t1 > T || t0 > t1 || out_every < 0) {
@@ -63,8 +64,10 @@ extern "C" int pf_fo_run(const pf_model* m, int64_t nk, const double* k_dev, con
     if (t0 > 0 && !state_dev) { set_error("pf_fo_run: a window with t0 > 0 needs state_dev"); return PF_E_ARG; }
     if (out_every > 0 && !yout_dev) { set_error("pf_fo_run: out_every > 0 needs yout_dev"); return PF_E_ARG; }
     if (layout != PF_LAYOUT_FULL && layout != PF_LAYOUT_PERT) { set_error("pf_fo_run: unknown layout %d", layout); return PF_E_ARG; }
+    if (out_pitch != 0 && out_pitch < nk) { set_error("pf_fo_run: out_pitch=%lld is smaller than nk=%lld", (long long)out_pitch, (long long)nk); return PF_E_ARG; }
     FoArgs a;
     a.layout = layout;
+    a.opitch = out_pitch ? out_pitch : nk;
     a.nk = nk; a.k = k_dev; a.tsix = tsix_dev; a.ystart = ystart_dev; a.rec = rec_dev;
     a.T = T; a.t0 = t0; a.t1 = t1; a.state = state_dev;
     a.yout = out_every > 0 ? yout_dev : nullptr; a.out_every = out_every; a.flags = flags_dev;
@@ -99,7 +102,7 @@ extern "C" int pf_fo_solve(const pf_model* m, int64_t nk, const double* k_dev, c
                            const double* ystart_dev, int64_t n0, const double* y0_host, int64_t T,
                            double simtstart, double h, int64_t t1, double* scratch_dev,
                            double* state_dev, double* yout_dev, int64_t out_every, int32_t layout,
-                           int32_t* ws_dev, void* stream) {
+                           int64_t out_pitch, int32_t* ws_dev, void* stream) {
     int rc = check_model(m);
     if (rc) return rc;
     if (nk < 0 || T < 1 || t1 < 0 || t1 > T || out_every < 0) { set_error("pf_fo_solve: bad sizes"); return PF_E_ARG; }
@@ -109,6 +112,7 @@ extern "C" int pf_fo_solve(const pf_model* m, int64_t nk, const double* k_dev, c
     if (nk > 0 && (!k_dev || !tsix_dev || !ystart_dev)) { set_error("pf_fo_solve: null buffer"); return PF_E_ARG; }
     if (out_every > 0 && !yout_dev) { set_error("pf_fo_solve: out_every > 0 needs yout_dev"); return PF_E_ARG; }
     if (layout != PF_LAYOUT_FULL && layout != PF_LAYOUT_PERT) { set_error("pf_fo_solve: unknown layout %d", layout); return PF_E_ARG; }
+    if (out_pitch != 0 && out_pitch < nk) { set_error("pf_fo_solve: out_pitch=%lld is smaller than nk=%lld", (long long)out_pitch, (long long)nk); return PF_E_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     const int nf = m->nfields;
     double* rec = scratch_dev;
@@ -121,7 +125,7 @@ extern "C" int pf_fo_solve(const pf_model* m, int64_t nk, const double* k_dev, c
         a.nk = nk; a.k = k_dev; a.tsix = tsix_dev; a.ystart = ystart_dev; a.rec = rec;
         a.T = T; a.t0 = 0; a.t1 = t1; a.state = state_dev;
         a.yout = out_every > 0 ? yout_dev : nullptr; a.out_every = out_every;
-        a.flags = ws_dev + 1; a.h = h; a.layout = layout;
+        a.flags = ws_dev + 1; a.h = h; a.layout = layout; a.opitch = out_pitch ? out_pitch : nk;
         if (launch_fo1_fused(m, a, simtstart, n0, y0_host, rec, ws_dev, st)) {
             PF_CUDA_CHECK(cudaGetLastError(), "pf_fo_solve fused launch");
             return PF_OK;
@@ -132,7 +136,7 @@ extern "C" int pf_fo_solve(const pf_model* m, int64_t nk, const double* k_dev, c
         a.nk = nk; a.k = k_dev; a.tsix = tsix_dev; a.ystart = ystart_dev; a.rec = rec;
         a.T = T; a.t0 = 0; a.t1 = t1; a.state = state_dev;
         a.yout = out_every > 0 ? yout_dev : nullptr; a.out_every = out_every;
-        a.flags = ws_dev + 1; a.h = h; a.layout = layout;
+        a.flags = ws_dev + 1; a.h = h; a.layout = layout; a.opitch = out_pitch ? out_pitch : nk;
         if (launch_fo_fused_generic(m, a, simtstart, n0, y0_host, rec, stagey, ws_dev, st)) {
             PF_CUDA_CHECK(cudaGetLastError(), "pf_fo_solve fused launch");
             return PF_OK;
@@ -143,5 +147,5 @@ extern "C" int pf_fo_solve(const pf_model* m, int64_t nk, const double* k_dev, c
     rc = pf_stage_table(m, T, simtstart, h, n0, bg, stagey, rec, stream);
     if (rc) return rc;
     return pf_fo_run(m, nk, k_dev, tsix_dev, ystart_dev, rec, T, h, 0, t1, state_dev, yout_dev, out_every,
-                     layout, ws_dev + 1, stream);
+                     layout, out_pitch, ws_dev + 1, stream);
 }

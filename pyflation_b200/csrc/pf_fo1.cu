@@ -157,7 +157,8 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
     const double h = a.h, hh = h * 0.5, h6 = h / 6.0;         // rk4.py:31-32
     const double2 nan2 = make_double2(qnan(), qnan());
     double2* prow = reinterpret_cast<double2*>(a.yout) + kk;  // row t0, var 0, this thread's k
-    const int64_t rstride = NV * nk;
+    const int64_t op = a.opitch;                              // modes per output row (>= nk)
+    const int64_t rstride = NV * op;
 
     // ---- regime 1: rows before any mode of this CTA starts: NaN+NaNj, no records needed.
     // Rows are stored when (n - t0) is a multiple of out_every (0: never); next_out tracks it.
@@ -168,7 +169,7 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
         for (int64_t r = a.t0; r < nan_end; ++r) {            // every == 1 in lock-step launches
             if (live) {
 #pragma unroll
-                for (int var = 0; var < NV; ++var) __stcs(prow + var * nk, nan2);
+                for (int var = 0; var < NV; ++var) __stcs(prow + var * op, nan2);
             }
             prow += rstride;
             if ((r - a.t0) % ls.rows == ls.rows - 1) lockstep_barrier(ls, r - a.t0);
@@ -178,7 +179,7 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
         for (; next_out < nan_end; next_out += every) {
             if (live) {
 #pragma unroll
-                for (int var = 0; var < NV; ++var) __stcs(prow + var * nk, nan2);
+                for (int var = 0; var < NV; ++var) __stcs(prow + var * op, nan2);
             }
             prow += rstride;
         }
@@ -221,11 +222,11 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
                 if (live && out) {
                     if constexpr (!PERT) {
                         __stcs(prow, make_double2(cf.bg[0], 0.0));
-                        __stcs(prow + nk, make_double2(cf.bg[1], 0.0));
-                        __stcs(prow + 2 * nk, make_double2(cf.bg[2], 0.0));
+                        __stcs(prow + op, make_double2(cf.bg[1], 0.0));
+                        __stcs(prow + 2 * op, make_double2(cf.bg[2], 0.0));
                     }
-                    __stcs(prow + XO * nk, make_double2(x[0], x[1]));
-                    __stcs(prow + (XO + 1) * nk, make_double2(v[0], v[1]));
+                    __stcs(prow + XO * op, make_double2(x[0], x[1]));
+                    __stcs(prow + (XO + 1) * op, make_double2(v[0], v[1]));
                 }
                 if (n + 1 < a.T) rk4_mode(cf, kval, h, hh, h6, x, v);
             } else if (live) {
@@ -233,7 +234,7 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
                 if (n < ts) {
                     if (out) {
 #pragma unroll
-                        for (int var = 0; var < NV; ++var) __stcs(prow + var * nk, nan2);   // rk4.py:100
+                        for (int var = 0; var < NV; ++var) __stcs(prow + var * op, nan2);   // rk4.py:100
                     }
                 } else {
                     double2 b0 = make_double2(cf.bg[0], 0.0), b1 = make_double2(cf.bg[1], 0.0),
@@ -254,11 +255,11 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
                     if (out) {
                         if constexpr (!PERT) {
                             __stcs(prow, b0);
-                            __stcs(prow + nk, b1);
-                            __stcs(prow + 2 * nk, b2);
+                            __stcs(prow + op, b1);
+                            __stcs(prow + 2 * op, b2);
                         }
-                        __stcs(prow + XO * nk, make_double2(x[0], x[1]));
-                        __stcs(prow + (XO + 1) * nk, make_double2(v[0], v[1]));
+                        __stcs(prow + XO * op, make_double2(x[0], x[1]));
+                        __stcs(prow + (XO + 1) * op, make_double2(v[0], v[1]));
                     }
                     if (n + 1 < a.T) rk4_mode(cf, kval, h, hh, h6, x, v);
                 }

@@ -262,6 +262,7 @@ __device__ __forceinline__ void fo_consume(const FoArgs& a, int64_t bx, int j, c
     const int64_t kk = bx * KPB + kl;
     const bool live = kk < a.nk;
     const int64_t nk = a.nk;
+    const int64_t op = a.opitch;                      // modes per output row (>= nk)
 
     const int64_t nsteps = a.t1 - a.t0;
     const int64_t nchunks = (nsteps + CH - 1) / CH;
@@ -327,15 +328,15 @@ __device__ __forceinline__ void fo_consume(const FoArgs& a, int64_t bx, int j, c
 #pragma unroll
                     for (int cc = 0; cc < NC; ++cc) nn[cc] = nan;
                     if (!pert) {
-                        store_row<NC>(orow + 2 * (int64_t)(2 * j) * nk, kk, part, nn);
-                        store_row<NC>(orow + 2 * (int64_t)(2 * j + 1) * nk, kk, part, nn);
-                        if (j == 0) store_row<NC>(orow + 2 * (int64_t)(2 * NF) * nk, kk, part, nn);
+                        store_row<NC>(orow + 2 * (int64_t)(2 * j) * op, kk, part, nn);
+                        store_row<NC>(orow + 2 * (int64_t)(2 * j + 1) * op, kk, part, nn);
+                        if (j == 0) store_row<NC>(orow + 2 * (int64_t)(2 * NF) * op, kk, part, nn);
                     }
 #pragma unroll
                     for (int i = 0; i < NF; ++i) {
                         const int64_t row = RO + NB + 2 * (i * NF + j);
-                        store_row<NC>(orow + 2 * row * nk, kk, part, nn);
-                        store_row<NC>(orow + 2 * (row + 1) * nk, kk, part, nn);
+                        store_row<NC>(orow + 2 * row * op, kk, part, nn);
+                        store_row<NC>(orow + 2 * (row + 1) * op, kk, part, nn);
                     }
                 }
             } else {
@@ -376,15 +377,15 @@ __device__ __forceinline__ void fo_consume(const FoArgs& a, int64_t bx, int j, c
                 }
                 if (out) {
                     if (!pert) {
-                        store_row<NC>(orow + 2 * (int64_t)(2 * j) * nk, kk, part, bgv[0]);
-                        store_row<NC>(orow + 2 * (int64_t)(2 * j + 1) * nk, kk, part, bgv[1]);
-                        if (j == 0) store_row<NC>(orow + 2 * (int64_t)(2 * NF) * nk, kk, part, bgv[2]);
+                        store_row<NC>(orow + 2 * (int64_t)(2 * j) * op, kk, part, bgv[0]);
+                        store_row<NC>(orow + 2 * (int64_t)(2 * j + 1) * op, kk, part, bgv[1]);
+                        if (j == 0) store_row<NC>(orow + 2 * (int64_t)(2 * NF) * op, kk, part, bgv[2]);
                     }
 #pragma unroll
                     for (int i = 0; i < NF; ++i) {
                         const int64_t row = RO + NB + 2 * (i * NF + j);
-                        store_row<NC>(orow + 2 * row * nk, kk, part, x[i]);
-                        store_row<NC>(orow + 2 * (row + 1) * nk, kk, part, v[i]);
+                        store_row<NC>(orow + 2 * row * op, kk, part, x[i]);
+                        store_row<NC>(orow + 2 * (row + 1) * op, kk, part, v[i]);
                     }
                 }
                 if (n + 1 < a.T) {
@@ -436,7 +437,7 @@ __device__ __forceinline__ void fo_consume(const FoArgs& a, int64_t bx, int j, c
             }
             if (out) {
                 next_out += a.out_every;
-                orow += 2 * (int64_t)NV * nk;
+                orow += 2 * (int64_t)NV * op;
             }
         }
         __syncthreads();                              // everyone is done reading srec[buf]

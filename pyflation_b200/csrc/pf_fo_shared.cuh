@@ -12,7 +12,9 @@ struct FoArgs {
     const double* __restrict__ rec;      // [T][REC]
     int64_t T, t0, t1;
     double* __restrict__ state;          // c128 [2 nf^2][nk]
-    double* __restrict__ yout;           // c128 [rows][nvar][nk]
+    double* __restrict__ yout;           // c128 [rows][nvar][opitch], this batch at columns [0, nk)
+    int64_t opitch;                      // modes per output row: nk, or the width of the assembled
+                                         // multi-GPU result this slab is written into
     int64_t out_every;
     int32_t* flags;
     double h;

@@ -52,7 +52,11 @@ def make_model(potential_func, pot_params, nfields, ainit=1.0):
 
 
 def _ptr(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+    if t is None:
+        return ctypes.c_void_p(0)
+    if isinstance(t, int):                              # raw device address (peer memory)
+        return ctypes.c_void_p(t)
+    return ctypes.c_void_p(t.data_ptr())
 
 
 def _stream_ptr(stream=None):
@@ -126,9 +130,11 @@ class FirstOrderProblem(object):
         self.bg, self.rec = background_tables(self.model, y0, self.T, self.h, self.simtstart,
                                               n0, True, self.dev)
 
-    def solve(self, y0, n0, t1, yout, out_every=1, stream=None, layout=0):
+    def solve(self, y0, n0, t1, yout, out_every=1, stream=None, layout=0, out_pitch=0):
         """pf_fo_solve: K1 + K1b + K2 for the window [0, t1) -- one fused launch for single-field
-        full-trajectory runs.  Leaves the step records in ``self.rec`` for later windows."""
+        full-trajectory runs.  Leaves the step records in ``self.rec`` for later windows.
+        ``yout`` is a device tensor or a raw device address (int: peer memory of a fused
+        gather, with ``out_pitch`` = width of the assembled result)."""
         L = _lib.lib()
         nf = self.nf
         y0 = np.ascontiguousarray(np.asarray(y0, dtype=np.float64).reshape(-1))
@@ -144,17 +150,17 @@ class FirstOrderProblem(object):
                                      self.simtstart, self.h, int(t1), _ptr(self.scratch),
                                      _ptr(self.state), _ptr(yout),
                                      int(out_every if yout is not None else 0), int(layout),
-                                     _ptr(self.ws), _stream_ptr(stream)))
+                                     int(out_pitch), _ptr(self.ws), _stream_ptr(stream)))
         nrec = int(L.pf_rec_doubles(nf))
         self.rec = self.scratch[:self.T * nrec].view(self.T, nrec)
 
-    def launch(self, t0, t1, yout, out_every=1, stream=None, layout=0):
-        """K2: rows [t0, t1) -> yout (device c128 tensor or None)."""
+    def launch(self, t0, t1, yout, out_every=1, stream=None, layout=0, out_pitch=0):
+        """K2: rows [t0, t1) -> yout (device c128 tensor, raw device address, or None)."""
         L = _lib.lib()
         _lib.check(L.pf_fo_run(ctypes.byref(self.model), self.nk, _ptr(self.k), _ptr(self.tsix),
                                _ptr(self.ystart), _ptr(self.rec), self.T, self.h, int(t0), int(t1),
                                _ptr(self.state), _ptr(yout), int(out_every if yout is not None else 0),
-                               int(layout), _ptr(self.flags), _stream_ptr(stream)))
+                               int(layout), int(out_pitch), _ptr(self.flags), _stream_ptr(stream)))
 
     def check_flags(self):
         f = int(self.flags.item())

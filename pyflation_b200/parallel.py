@@ -97,6 +97,86 @@ def gather_rows(rows_local, bounds, group=None):
     return full
 
 
+class _DeviceArray(object):
+    """Raw device memory described through ``__cuda_array_interface__`` so that torch can wrap
+    it (complex128, C order) without owning it."""
+
+    def __init__(self, ptr, shape, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(int(s) for s in shape), "typestr": "<c16",
+                                         "data": (int(ptr), False), "version": 3, "strides": None}
+        self._owner = owner
+
+
+class PeerAssembly(object):
+    """The assembled result [rows][nvar][nk] of a k-sharded run, living on rank ``root`` and
+    written DIRECTLY by every rank's mode kernel: each rank maps the root's buffer (CUDA IPC,
+    ``pf_peer_*``) and passes ``&assembled[0][0][k0]`` with ``out_pitch = nk`` to
+    ``pf_fo_solve`` / ``pf_fo_run``, so the k-gather rides on the kernel's own 128-bit stores
+    over NVLink / NVSwitch, row by row as they are produced, instead of an all-gather plus an
+    interleave pass after the integration (``gather_rows``).
+
+    All ranks of the group must construct it (collective: one 64-byte broadcast)."""
+
+    def __init__(self, rows, nvar, nk, root=0, group=None):
+        L = _lib.lib()
+        self.shape = (int(rows), int(nvar), int(nk))
+        self.nbytes = int(rows) * int(nvar) * int(nk) * 16
+        self.root = root
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.owner = self.rank == root
+        self.base = None
+        # the handle travels as a 64-byte tensor: on the GPU for NCCL, on the host for gloo
+        on_host = self.world > 1 and dist.get_backend(group) == "gloo"
+        dev = torch.device("cpu") if on_host else torch.device("cuda", torch.cuda.current_device())
+        handle = torch.zeros(_lib.PF_PEER_HANDLE_BYTES, dtype=torch.uint8, device=dev)
+        if self.owner:
+            p = ctypes.c_void_p()
+            _lib.check(L.pf_peer_alloc(self.nbytes, ctypes.byref(p)))
+            self.base = int(p.value)
+            if self.world > 1:
+                buf = ctypes.create_string_buffer(_lib.PF_PEER_HANDLE_BYTES)
+                _lib.check(L.pf_peer_export(ctypes.c_void_p(self.base), buf))
+                handle.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+        if self.world > 1:
+            dist.broadcast(handle, src=dist.get_global_rank(group, root) if group is not None else root,
+                           group=group)
+            if not self.owner:
+                raw = handle.cpu().numpy().tobytes()
+                p = ctypes.c_void_p()
+                _lib.check(L.pf_peer_open(raw, ctypes.byref(p)))
+                self.base = int(p.value)
+
+    def column_ptr(self, k0):
+        """Device address of assembled[0][0][k0] in this rank's address space."""
+        return self.base + 16 * int(k0)
+
+    def complete(self, stream=None):
+        """Wait until every rank's stores have landed: stream sync on each writer, then a barrier."""
+        (stream or torch.cuda.current_stream()).synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def tensor(self):
+        """The assembled array as a CUDA tensor (root only; valid until ``close``)."""
+        if not self.owner:
+            raise RuntimeError("only the root rank holds the assembled result")
+        return torch.as_tensor(_DeviceArray(self.base, self.shape, self), device="cuda")
+
+    def close(self):
+        if self.base is None:
+            return
+        L = _lib.lib()
+        if self.world > 1:
+            dist.barrier(group=self.group)               # nobody closes while a peer still writes
+        if self.owner:
+            _lib.check(L.pf_peer_free(ctypes.c_void_p(self.base)))
+        else:
+            _lib.check(L.pf_peer_close(ctypes.c_void_p(self.base)))
+        self.base = None
+
+
 def gather_spectrum(pr_local, bounds, group=None):
     """All-gather a per-mode quantity [R][nk_r] (e.g. P_R of the last row) into [R][nk]."""
     return gather_rows(pr_local.unsqueeze(1), bounds, group)[:, 0, :]
@@ -144,6 +224,46 @@ class ShardedFirstOrder(object):
         m = self.model if self.model is not None else self.prepare()
         m.runfo()
         return m
+
+    def problem(self):
+        """This rank's slab as a device problem (start vectors from the host IC glue, bit-identical
+        to the reference's) plus column 0's background start (y0, n0)."""
+        from . import engine
+        m = self.model if self.model is not None else self.prepare()
+        nf = m.nfields
+        T = int(np.around((m.fotend - m.simtstart) / m.tstep_wanted) + 1)
+        pm = engine.make_model(m.potential_func, m.pot_params, nf, m.ainit)
+        prob = engine.FirstOrderProblem(pm, m.k, m.fotstartindex, m.foystart, m.simtstart, T,
+                                        m.tstep_wanted)
+        return prob, np.real(m.foystart[0:2 * nf + 1, 0]).copy(), int(m.fotstartindex.min())
+
+    def run_assembled(self, out_every=1, root=0, fused=True, prob=None, assembly=None):
+        """Integrate this rank's slab and assemble rows 0, s, 2s, ... of the GLOBAL yresult
+        ([R][nvar][nk], k innermost -- rank slabs interleave row by row, rk4.py:95-100) on rank
+        ``root``.
+
+        fused=True : every rank's kernel stores straight into the root's buffer over NVLink
+                     (PeerAssembly); returns (tensor on root / None elsewhere, assembly).
+        fused=False: local slab, then NCCL all-gather + interleave (``gather_rows``); returns
+                     (tensor on every rank, None)."""
+        from . import engine
+        if prob is None:
+            prob, y0, n0 = self.problem()
+        else:
+            prob, y0, n0 = prob
+        nk = int(self.bounds[-1])
+        R = (prob.T + out_every - 1) // out_every
+        if not fused:
+            local = engine.first_order_device(prob, out_every=out_every, y0=y0, n0=n0)
+            prob.check_flags()
+            return (gather_rows(local, self.bounds) if self.world > 1 else local), None
+        asm = assembly if assembly is not None else PeerAssembly(R, prob.nvar, nk, root=root)
+        with torch.cuda.device(prob.dev):
+            prob.solve(y0, n0, prob.T, asm.column_ptr(self.bounds[self.rank]), out_every,
+                       out_pitch=nk)
+        asm.complete()
+        prob.check_flags()
+        return (asm.tensor() if asm.owner else None), asm
 
 
 def sharded_spectrum_run(potential_func, k, gather=True, **kwargs):

@@ -1,6 +1,12 @@
-"""Worker of tests/test_multigpu.py: run under torchrun with >= 2 ranks, one GPU each.
-Shards a first-order run over the ranks, gathers result rows with NCCL and checks them against
-an unsharded run of the same grid done by rank 0."""
+"""Worker of tests/test_multigpu.py: run under torchrun with >= 2 ranks.
+
+Default: one GPU per rank, NCCL.  Shards a first-order run over the ranks and checks, against an
+unsharded run of the same grid done by rank 0,
+  * the NCCL path: local slabs -> all-gather + pf_scatter_slab (parallel.gather_rows), and
+  * the fused path: every rank's kernel stores its columns straight into rank 0's assembled
+    array through peer memory (parallel.PeerAssembly, pf_peer_*, out_pitch).
+``--same-gpu``: every rank uses cuda:0 and the control plane is gloo (NCCL refuses two ranks on
+one device); the fused path then runs for real through CUDA IPC on a single-GPU box."""
 import os
 import sys
 
@@ -12,38 +18,58 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
 
 
+def compare(got, want):
+    same_nan = np.array_equal(np.isnan(got), np.isnan(want))
+    fin = ~np.isnan(want)
+    scale = np.nanmax(np.abs(want), axis=1, keepdims=True) * np.ones_like(want.real)
+    return same_nan, float((np.abs(got[fin] - want[fin]) / scale[fin]).max())
+
+
 def main():
+    same_gpu = "--same-gpu" in sys.argv
     rank = int(os.environ["RANK"])
-    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    torch.cuda.set_device(0 if same_gpu else int(os.environ["LOCAL_RANK"]))
     os.environ.setdefault("NCCL_DEBUG", "WARN")
-    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    if same_gpu:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
     from pyflation_b200 import cosmomodels as c, parallel
-    k = np.linspace(0.85e-60, 8.2165e-58, 3001)
-    kw = dict(potential_func="hybridquadratic", pot_params={"nfields": 2}, nfields=2,
-              bgystart=np.array([12.0, 1 / 300.0, 12.0, 49 / 300.0, 0]), cq=50)
-    sh = parallel.ShardedFirstOrder(k=k, **kw)
-    m = sh.run()
-    sl = parallel.my_slab(sh.bounds)
-    assert m.yresult.shape[2] == sl.stop - sl.start
-    rows = [100, 2000, m.yresult.shape[0] - 1]
-    local = torch.as_tensor(np.ascontiguousarray(m.yresult[rows]), device="cuda")
-    full = parallel.gather_rows(local, sh.bounds)                 # NCCL all-gather + pf_scatter_slab
-    pr_local = torch.as_tensor(m.Pr[-1:], device="cuda")
-    pr_full = parallel.gather_spectrum(pr_local, sh.bounds)
     ok = True
+    report = []
+    for pot, nf, bgy, nk in (("hybridquadratic", 2, [12.0, 1 / 300.0, 12.0, 49 / 300.0, 0], 3001),
+                             ("msqphisq", 1, [18.0, -0.1, 0.0], 20011)):
+        k = np.linspace(0.85e-60, 8.2165e-58, nk)
+        kw = dict(potential_func=pot, pot_params={"nfields": nf}, nfields=nf, bgystart=np.array(bgy), cq=50)
+        sh = parallel.ShardedFirstOrder(k=k, full_output=False, **kw)
+        sh.prepare()
+        stride = 97
+        fused, asm = sh.run_assembled(out_every=stride, root=0, fused=True)
+        gathered = None
+        if not same_gpu:
+            gathered, _ = sh.run_assembled(out_every=stride, fused=False)
+            m = sh.run()
+            pr_full = parallel.gather_spectrum(torch.as_tensor(m.Pr[-1:], device="cuda"), sh.bounds)
+        if rank == 0:
+            ref = c.FOCanonicalTwoStage(k=k, **kw)
+            ref.run(saveresults=False)
+            want = ref.yresult[::stride]
+            nan_f, err_f = compare(fused.cpu().numpy(), want)
+            good = nan_f and err_f < 1e-11
+            line = "%s nf=%d nk=%d bounds=%s fused err=%.2e" % (pot, nf, nk, sh.bounds.tolist(), err_f)
+            if gathered is not None:
+                nan_g, err_g = compare(gathered.cpu().numpy(), want)
+                err_pr = float(np.max(np.abs(pr_full.cpu().numpy() / ref.Pr[-1:] - 1)))
+                # the two assembly paths run the same kernel on the same inputs: same bits
+                bits = torch.equal(torch.view_as_real(fused).nan_to_num(0.0), torch.view_as_real(gathered).nan_to_num(0.0))
+                good = good and nan_g and err_g < 1e-11 and err_pr < 1e-11 and bits
+                line += " nccl err=%.2e P_R err=%.2e fused==nccl bits %s" % (err_g, err_pr, bits)
+            report.append(line)
+            ok = ok and good
+        asm.close()
     if rank == 0:
-        ref = c.FOCanonicalTwoStage(k=k, **kw)
-        ref.run(saveresults=False)
-        want = ref.yresult[rows]
-        got = full.cpu().numpy()
-        same_nan = np.array_equal(np.isnan(got), np.isnan(want))
-        fin = ~np.isnan(want)
-        scale = np.nanmax(np.abs(want), axis=1, keepdims=True) * np.ones_like(want.real)
-        err = float((np.abs(got[fin] - want[fin]) / scale[fin]).max())
-        err_pr = float(np.max(np.abs(pr_full.cpu().numpy() / ref.Pr[-1:] - 1)))
-        ok = same_nan and err < 1e-11 and err_pr < 1e-11
-        print("multigpu_check world=%d bounds=%s rows err=%.2e P_R err=%.2e %s"
-              % (dist.get_world_size(), sh.bounds.tolist(), err, err_pr, "OK" if ok else "FAIL"))
+        print("multigpu_check world=%d %s\n  " % (dist.get_world_size(), "same-gpu/gloo" if same_gpu else "nccl")
+              + "\n  ".join(report) + "\n" + ("OK" if ok else "FAIL"))
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

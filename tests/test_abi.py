@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(L, name), "missing export %s" % name
     assert sorted(_lib.EXPORTS) == names
-    assert _lib.lib().pf_version() == 1
+    assert _lib.lib().pf_version() == 2
 
 
 def test_potential_table_matches_reference_defaults(oracle):

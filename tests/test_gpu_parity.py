@@ -303,7 +303,7 @@ def test_edge_cases_and_errors():
     m, prob = _problem(g)
     from pyflation_b200 import _lib
     assert _lib.lib().pf_fo_run(ctypes.byref(prob.model), 0, None, None, None, None, prob.T, 0.01, 0, prob.T,
-                                None, None, 0, 0, None, None) == 0
+                                None, None, 0, 0, 0, None, None) == 0
     # column 0 must start first (the reference NaN-poisons such runs, cosmomodels.py:641)
     fo = c.CanonicalFirstOrder(k=m.k[::-1].copy(), ainit=m.ainit, ystart=m.foystart[:, ::-1].copy(),
                                tstartindex=m.fotstartindex[::-1].copy(), tend=m.fotend,

@@ -1,5 +1,11 @@
-"""NCCL path of the k-sharded run (needs >= 2 GPUs; skipped on a single-GPU box, where the gloo
-world-size-2 test in test_distributed.py covers the host logic)."""
+"""Multi-rank assembly of a k-sharded run (tests/multigpu_worker.py under torchrun).
+
+* ``test_fused_assembly_two_ranks`` always runs: on a single-GPU box the two ranks share cuda:0
+  (gloo control plane) and the fused gather -- every rank's kernel storing its columns into
+  rank 0's array through CUDA-IPC peer memory -- is exercised for real.
+* ``test_sharded_run_and_nccl_gather`` needs >= 2 GPUs: NCCL all-gather path and fused path
+  over NVLink, bit-compared with each other and checked against an unsharded run.
+The gloo world-size-2 test in test_distributed.py covers the host logic on CPU."""
 import os
 import subprocess
 import sys
@@ -11,15 +17,31 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
+def _torchrun(world, port, *extra):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tests", "multigpu_worker.py")] + list(extra)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "OK" in res.stdout
+    return res.stdout
+
+
+def test_fused_assembly_two_ranks():
+    import torch
+    if torch.cuda.device_count() >= 2:
+        out = _torchrun(2, 29534)
+        assert "fused==nccl bits True" in out
+    else:
+        _torchrun(2, 29534, "--same-gpu")
+
+
 def test_sharded_run_and_nccl_gather():
     import torch
     n = torch.cuda.device_count()
     if n < 2:
-        pytest.skip("needs at least 2 GPUs")
+        pytest.skip("NCCL needs one GPU per rank; the fused assembly is covered by "
+                    "test_fused_assembly_two_ranks on this box")
     world = 2 if n < 4 else 4
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-           "--master-addr", "127.0.0.1", "--master-port", "29533",
-           os.path.join(ROOT, "tests", "multigpu_worker.py")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
-    assert "OK" in res.stdout
+    out = _torchrun(world, 29533)
+    assert "fused==nccl bits True" in out
