@@ -16,6 +16,16 @@ stage table (K1b) and the mode kernel (K2) writing yresult[T][5][nk] into HBM.
   cpu_baseline / --impl reference : the NumPy oracle port of the reference's rkdriver_tsix +
            CanonicalFirstOrder.derivs on the host cores, one process per core, each on a
            contiguous k-shard of a bounded sample of the same workload.
+  configs  : (N = 1) every other BASELINE.json configuration, a few launches each after the
+           headline loop: value, ms and its own roofline (HBM against MEASURED_PEAKS.json, fp64
+           against a DFMA probe run in this process).
+  strong / e2e_spectrum / collective : BASELINE configs[4] -- a fixed 2^24-mode msqphisq grid
+           sharded over the N ranks (device-resident pipeline, P_R(k) gathered with NCCL); the
+           same pipeline from a host k array to a host P_R(k) array, 2^22 modes per GPU; and,
+           for N > 1, the assembly of a strided yresult of the 2^20-mode grid on rank 0 -- once
+           as local slabs + NCCL all-gather + interleave, once with every rank's kernel storing
+           its columns straight into rank 0's array over NVLink (PeerAssembly) -- both checked
+           in-run against the reference's golden columns (tests/golden/fo_c5_msqphisq_2p20.npz).
 """
 import argparse
 import json
@@ -195,6 +205,264 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------
+# the other BASELINE configurations (N = 1), config 5 (every N), the collective (N > 1)
+# ------------------------------------------------------------------------------------------
+FLOPS_PER_MODE_STEP = {1: 104, 2: 456, 8: 13320}          # nf^2 (80 + 16 nf) + 8
+
+
+def _k4_grid():
+    from pyflation_b200 import helpers
+    return helpers.seq(KMIN, helpers.getkend(0.85e-60, 0.4e-60, 1025), 0.4e-60)
+
+
+# name, potential, nfields, pot_params, bgystart, k grid, out_every ("last" = rows 0 and T-1)
+EXTRA_CONFIGS = [
+    ("configs[0] msqphisq, default 2053-mode grid, full trajectory", "msqphisq", 1, {"nfields": 1},
+     [18.0, -0.1, 0.0], "K4", 1),
+    ("configs[2] hybridquadratic nf=2, 2^16 modes, full trajectory (100 GB)", "hybridquadratic", 2,
+     {"nfields": 2}, [12.0, 1 / 300.0, 12.0, 49 / 300.0, 0.0], 2 ** 16, 1),
+    ("configs[2] hybridquadratic nf=2, 2^20 modes, every 64th row", "hybridquadratic", 2,
+     {"nfields": 2}, [12.0, 1 / 300.0, 12.0, 49 / 300.0, 0.0], 2 ** 20, 64),
+    ("configs[3] nflation nf=8, 2^18 modes, every 512th row", "nflation", 8, {"nfields": 8}, None,
+     2 ** 18, 512),
+    ("configs[3] nflation nf=8, 2^13 modes, full trajectory (155 GB)", "nflation", 8, {"nfields": 8},
+     None, 2 ** 13, 1),
+    ("configs[4] msqphisq, 2^20 modes (one GPU's slab), last row only", "msqphisq", 1, {"nfields": 1},
+     [18.0, -0.1, 0.0], 2 ** 20, "last"),
+]
+
+
+def _events(n):
+    import torch
+    return [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+
+
+def measure_extra_configs(hbm_peak, fp64_peak, reps=3):
+    """One entry per remaining BASELINE configuration: whole first-order solve (K1 + K1b + mode
+    kernel, the metric's definition) and the mode kernel alone, CUDA events, inputs in HBM."""
+    import torch
+    from pyflation_b200 import cosmomodels, engine
+    out_list = []
+    for name, pot, nf, params, bgy, grid, every in EXTRA_CONFIGS:
+        try:
+            k = _k4_grid() if grid == "K4" else np.linspace(KMIN, KMAX, grid)
+            m = cosmomodels.FOCanonicalTwoStage(k=k, potential_func=pot, pot_params=dict(params), nfields=nf,
+                                                bgystart=None if bgy is None else np.array(bgy), cq=CQ,
+                                                tend=TEND, tstep_wanted=H)
+            m.runbg()
+            m.setfoics()
+            T = int(np.around(m.fotend / H) + 1)
+            pm = engine.make_model(pot, params, nf, m.ainit)
+            prob = engine.FirstOrderProblem(pm, k, m.fotstartindex, m.foystart, 0.0, T, H)
+            n0 = int(m.fotstartindex.min())
+            y0 = np.real(m.foystart[0:2 * nf + 1, 0]).copy()
+            stride = max(1, T - 1) if every == "last" else int(every)
+            nrows = (T + stride - 1) // stride
+            nvar = prob.nvar
+            out = torch.empty((nrows, nvar, len(k)), dtype=torch.complex128, device="cuda")
+            mode_steps = float(np.sum(T - 1 - m.fotstartindex))
+            # rows actually written after a mode's start (the NaN prefix is not algorithmic work)
+            rows_t = np.arange(0, T, stride)
+            written = float(np.sum(len(rows_t) - np.searchsorted(rows_t, m.fotstartindex, side="left")))
+            for _ in range(1):
+                prob.solve(y0, n0, T, out, stride)
+            ev = _events(reps)
+            for a, b in ev:
+                a.record()
+                prob.solve(y0, n0, T, out, stride)
+                b.record()
+            torch.cuda.synchronize()
+            solve_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+            # the mode kernel alone, records already built (what the three-launch path and the
+            # stage-argument cache run); for nf <= 2 pf_fo_solve is ONE fused launch instead
+            prob.build_tables(y0, n0)
+            prob.launch(0, T, out, stride)
+            ev = _events(reps)
+            for a, b in ev:
+                a.record()
+                prob.launch(0, T, out, stride)
+                b.record()
+            torch.cuda.synchronize()
+            kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+            prob.check_flags()
+            last = out[nrows - 1:nrows] if (T - 1) % stride == 0 else None
+            if last is not None:
+                pr = engine.pr_spectrum_device(nf, last, prob.k)
+                assert bool(torch.isfinite(pr).all()) and float(pr.min()) > 0
+            best_ms = min(solve_ms, kernel_ms) if nf <= 2 else kernel_ms
+            alg_bytes = written * 16 * nvar
+            all_bytes = float(nrows) * nvar * len(k) * 16
+            flops = mode_steps * FLOPS_PER_MODE_STEP[nf]
+            f_hbm = alg_bytes / (best_ms * 1e-3) / 1e9 / hbm_peak
+            f_fp = flops / (best_ms * 1e-3) / 1e12 / fp64_peak
+            bound = "hbm" if f_hbm >= f_fp else "fp64"
+            entry = {"workload": name, "nk": int(len(k)), "T": T, "out_every": every,
+                     "value": mode_steps / (solve_ms * 1e-3), "ms": solve_ms,
+                     "mode_kernel_ms": kernel_ms, "mode_kernel_value": mode_steps / (kernel_ms * 1e-3),
+                     "output_policy": "full trajectory" if stride == 1 else
+                                      ("rows 0 and T-1" if every == "last" else "every %dth row" % stride),
+                     "roofline": {"bound": bound, "frac": max(f_hbm, f_fp),
+                                  "timed": "fused solve" if (nf <= 2 and solve_ms <= kernel_ms) else "mode kernel",
+                                  "hbm": {"achieved": alg_bytes / (best_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                                          "unit": "GB/s", "frac": f_hbm,
+                                          "achieved_all_rows": all_bytes / (best_ms * 1e-3) / 1e9,
+                                          "frac_all_rows": all_bytes / (best_ms * 1e-3) / 1e9 / hbm_peak},
+                                  "fp64": {"achieved": flops / (best_ms * 1e-3) / 1e12, "peak": fp64_peak,
+                                           "unit": "TFLOP/s", "frac": f_fp,
+                                           "flops_per_mode_step": FLOPS_PER_MODE_STEP[nf]}}}
+            if nf == 8:
+                entry["roofline"]["fp64"]["note"] = (
+                    "13320 flop per mode-step is SURVEY 8(d)'s dense formulation; the factored "
+                    "nflation kernel executes 10656 (5328 fp64 instructions), so its pipe "
+                    "utilisation is frac * 0.80")
+            if grid == "K4":
+                # with the stage arguments runbg() left on the device: K1b + mode kernel only
+                hit = engine.cached_stage_args(pm, H, 0.0, n0, y0, T, prob.dev)
+                if hit is not None:
+                    prob.use_stage_args(*hit)
+                    prob.solve(y0, n0, T, out, stride)
+                    ev = _events(reps)
+                    for a, b in ev:
+                        a.record()
+                        prob.use_stage_args(*hit)
+                        prob.solve(y0, n0, T, out, stride)
+                        b.record()
+                    torch.cuda.synchronize()
+                    cms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+                    entry["cached_background"] = {"ms": cms, "value": mode_steps / (cms * 1e-3),
+                                                  "what": "K1b + mode kernel from the stage arguments of runbg()"}
+            del out, prob
+            torch.cuda.empty_cache()
+            out_list.append(entry)
+        except Exception as err:                               # a config must not sink the bench line
+            out_list.append({"workload": name, "error": repr(err)})
+            torch.cuda.empty_cache()
+    return out_list
+
+
+def measure_config5(world, rank, barrier):
+    """BASELINE configs[4]: msqphisq, k-sharded, device-resident pipeline.
+    strong        : fixed 2^24-mode grid over the N ranks, P_R(k) gathered with NCCL.
+    e2e_spectrum  : host k array in -> host P_R(k) array out, 2^22 modes per GPU (weak)."""
+    import torch
+    import torch.distributed as dist
+    from pyflation_b200 import parallel
+    kw = dict(nfields=1, pot_params={"nfields": 1}, bgystart=np.array([18.0, -0.1, 0.0]), cq=CQ)
+    res = {}
+    for tag, nk in (("strong", 2 ** 24), ("e2e_spectrum", (2 ** 22) * world)):
+        k = np.linspace(KMIN, KMAX, nk)
+        wall = None
+        for rep in range(2):                                   # rep 0 warms allocator and NCCL
+            barrier()
+            t0 = time.perf_counter()
+            r = parallel.sharded_spectrum_run("msqphisq", k, gather=True, **kw)
+            if tag == "e2e_spectrum":
+                pr_host = r["scaled_Pr_all"][-1].cpu().numpy()
+            torch.cuda.synchronize()
+            barrier()
+            wall = time.perf_counter() - t0
+        steps = torch.tensor([float((r["T"] - 1 - r["fotstartindex"]).sum().item())], dtype=torch.float64,
+                             device="cuda")
+        tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(steps)
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        spr = r["scaled_Pr_all"][-1]
+        ok = bool(torch.isfinite(spr).all()) and float(spr.min()) > 0 and spr.shape[0] == nk
+        res[tag] = {"nk": nk, "n_gpus": world, "wall_s": float(tw[0]), "value": float(steps[0]) / float(tw[0]),
+                    "unit": UNIT, "scaled_Pr_first_last": [float(spr[0]), float(spr[-1])], "finite": ok,
+                    "what": ("whole device-resident pipeline (background, crossings, Bunch-Davies start "
+                             "vectors, integration, P_R, NCCL gather of P_R)" if tag == "strong" else
+                             "host k array -> sharded_spectrum_run -> host scaled P_R(k) array")}
+        if tag == "e2e_spectrum":
+            res[tag]["h2d_bytes"] = nk * 8
+            res[tag]["d2h_bytes"] = nk * 8
+            res[tag]["scaling"] = "weak (2^22 modes per GPU)"
+            assert pr_host.shape[0] == nk
+        del r
+        torch.cuda.empty_cache()
+    return res
+
+
+def measure_collective(world, rank, barrier):
+    """Assembly of a strided yresult of the 2^20-mode msqphisq grid on rank 0 (k innermost, so
+    rank slabs interleave row by row, rk4.py:95-100), timed on the device both ways and checked
+    against the reference's golden columns."""
+    import torch
+    import torch.distributed as dist
+    from pyflation_b200 import parallel
+    g = np.load(os.path.join(ROOT, "tests", "golden", "fo_c5_msqphisq_2p20.npz"))
+    nk, every = 2 ** 20, 40
+    k = np.linspace(KMIN, KMAX, nk)
+    assert np.array_equal(k[g["kix"]], g["k"])
+    sh = parallel.ShardedFirstOrder(k=k, full_output=False, potential_func="msqphisq",
+                                    pot_params={"nfields": 1}, nfields=1,
+                                    bgystart=np.array([18.0, -0.1, 0.0]), cq=CQ)
+    sh.prepare()
+    pack = sh.problem()
+    prob = pack[0]
+    R = (prob.T + every - 1) // every
+    nbytes = R * prob.nvar * nk * 16
+    out = {"op": "k-gather of yresult[::%d] (msqphisq, 2^20 modes) onto rank 0" % every, "nranks": world,
+           "bytes": nbytes, "rows": R}
+
+    def check(full):
+        sel = g["rows"][g["rows"] % every == 0]
+        got = full[torch.as_tensor(sel // every, device=full.device)][:, :, torch.as_tensor(g["kix"], device=full.device)]
+        got = got.cpu().numpy()
+        want = g["yrows"][np.isin(g["rows"], sel)]
+        assert np.array_equal(np.isnan(got), np.isnan(want)), "NaN layout differs from the golden columns"
+        fin = ~np.isnan(want)
+        scale = np.nanmax(np.abs(want[:, 3:]), axis=1, keepdims=True) * np.ones_like(want.real)
+        scale[:, :3] = np.abs(want[:, :3])
+        err = float((np.abs(got[fin] - want[fin]) / scale[fin]).max())
+        assert err < 1e-9, "gathered columns differ from the reference golden columns: %.3e" % err
+        return err
+
+    def timed(fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return r, float(t[0])
+
+    # compute only (local slab, no assembly) -- the floor both paths are compared with
+    from pyflation_b200 import engine
+    engine.first_order_device(prob, out_every=every, y0=pack[1], n0=pack[2])
+    _, ms_local = timed(lambda: engine.first_order_device(prob, out_every=every, y0=pack[1], n0=pack[2]))
+    # (a) NCCL: local slab, all-gather of padded slabs, on-GPU interleave
+    sh.run_assembled(out_every=every, fused=False, prob=pack)
+    (full_a, _), ms_nccl = timed(lambda: sh.run_assembled(out_every=every, fused=False, prob=pack))
+    if rank == 0:
+        out["parity_nccl_max_rel_err"] = check(full_a)
+    del full_a
+    torch.cuda.empty_cache()
+    # (b) fused: every rank's kernel stores its columns into rank 0's array over NVLink
+    asm = parallel.PeerAssembly(R, prob.nvar, nk, root=0)
+    sh.run_assembled(out_every=every, fused=True, prob=pack, assembly=asm)
+    (full_b, _), ms_fused = timed(lambda: sh.run_assembled(out_every=every, fused=True, prob=pack, assembly=asm))
+    if rank == 0:
+        out["parity_fused_max_rel_err"] = check(full_b)
+    del full_b
+    asm.close()
+    moved = nbytes * (world - 1) / world                       # bytes that cross NVLink into rank 0
+    out.update({"ms_compute_only": ms_local, "ms_nccl_allgather_path": ms_nccl, "ms_fused_peer_store_path": ms_fused,
+                "nvlink_bytes_into_root": moved,
+                "nccl_allgather_busbw_GBs": nbytes * (world - 1) / world / max(1e-9, (ms_nccl - ms_local) * 1e-3) / 1e9,
+                "fused_inbound_GBs": moved / (ms_fused * 1e-3) / 1e9,
+                "note": "all-gather path: every rank ends up with the full array (bus bandwidth = "
+                        "(N-1)/N * bytes / (t_path - t_compute)); fused path: gather onto rank 0 only, "
+                        "transfer overlapped with the integration row by row; NVLink 5 peak 900 GB/s "
+                        "per direction per GPU"})
+    return out
+
+
+# ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
 def run_gpu_arm(args):
@@ -312,6 +580,17 @@ def run_gpu_arm(args):
     del out
     torch.cuda.empty_cache()
 
+    # ---- the other BASELINE configurations, config 5, the collective
+    extras = {}
+    if not args.no_extras:
+        fp64_peak = engine.fp64_peak_tflops()
+        extras["fp64_peak_tflops"] = fp64_peak
+        if world == 1:
+            extras["configs"] = measure_extra_configs(peak, fp64_peak)
+        extras.update(measure_config5(world, rank, barrier))
+        if world > 1:
+            extras["collective"] = measure_collective(world, rank, barrier)
+
     # ---- e2e through the public API with host buffers
     e2e = None if args.no_e2e else run_e2e(args, m, T, nvar, mode_steps, world, rank, barrier)
 
@@ -325,6 +604,7 @@ def run_gpu_arm(args):
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "T": T, "mode_steps_per_gpu_step": mode_steps,
         }
+        line.update(extras)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -409,6 +689,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3, dest="e2e_steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the other configs / config-5 / collective phases (profiling runs)")
     ap.add_argument("--cpu-warmup", action="store_true")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ and args.impl == "ours":

@@ -192,6 +192,13 @@ int pf_bunch_davies(int nfields, int64_t nk, const double *k_dev, const int64_t 
  * scaled spectrum k^3/(2 pi^2) P_R (utilities.py:12-37). */
 int pf_pr_spectrum(int nfields, int64_t nrows, int64_t nk, const double *y_dev,
                    const double *k_dev, double *Pr_dev, void *stream);
+/* The same for a PF_LAYOUT_PERT window pert_dev c128 [nrows][2 nf^2][nk] holding rows
+ * t0 .. t0+nrows-1: phi'_I is read from the background row inside the step records
+ * (rec_dev[t][rec_pitch], background row at column bg_off).  Lets a host-bound solve reduce
+ * P_R on each device window before it is recycled, instead of re-uploading the trajectory. */
+int pf_pr_spectrum_pert(int nfields, int64_t nrows, int64_t nk, const double *pert_dev,
+                        const double *rec_dev, int64_t rec_pitch, int64_t bg_off, int64_t t0,
+                        const double *k_dev, double *Pr_dev, void *stream);
 
 /* ---- host-bound results: ship the perturbation rows over PCIe, rebuild the rest on the host ----
  * pf_copy_rows_d2h: asynchronous 2-D device->host copy (height rows of width_bytes each, with
@@ -215,6 +222,12 @@ int pf_host_fill_background(double *yout_host, int nfields, int64_t nk, int64_t 
  * column offset k0 (the on-GPU permute after an NCCL all-gather of slabs). */
 int pf_scatter_slab(int64_t nrows_times_nvar, int64_t nk_r, int64_t nk, int64_t k0,
                     const double *slab_dev, double *full_dev, void *stream);
+
+/* ---- measured fp64 peak (roofline denominator of the compute-bound configurations) ----
+ * Runs a DFMA saturation kernel (8 independent chains per thread, 8 x 256 threads per SM) on the
+ * default stream of the current device, synchronously, and returns the best of 3 timed launches
+ * in TFLOP/s (FMA = 2 flops).  scratch_dev: at least 8 * 256 * (number of SMs) doubles. */
+int pf_fp64_peak_probe(int iters, double *scratch_dev, int64_t scratch_doubles, double *tflops_out);
 
 /* ---- peer memory: the destination of a fused k-gather (one process per GPU, one box) ----
  * The rank that assembles a result allocates it with pf_peer_alloc (a dedicated cudaMalloc, so

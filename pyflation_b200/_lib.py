@@ -22,9 +22,9 @@ EXPORTS = [
     "pf_potential_nfields", "pf_potential_nparams", "pf_potential_param_name",
     "pf_potential_param_default", "pf_potential_eval", "pf_number_of_steps", "pf_nvar",
     "pf_rec_doubles", "pf_bg_run", "pf_stage_table", "pf_fo_run", "pf_solve_scratch_doubles",
-    "pf_fo_solve", "pf_pr_spectrum", "pf_scatter_slab", "pf_copy_rows_d2h",
+    "pf_fo_solve", "pf_pr_spectrum", "pf_pr_spectrum_pert", "pf_scatter_slab", "pf_copy_rows_d2h",
     "pf_host_fill_background", "pf_crossing_rows", "pf_bunch_davies", "pf_derivs",
-    "pf_peer_alloc", "pf_peer_free", "pf_peer_export", "pf_peer_open", "pf_peer_close",
+    "pf_fp64_peak_probe", "pf_peer_alloc", "pf_peer_free", "pf_peer_export", "pf_peer_open", "pf_peer_close",
 ]
 
 
@@ -94,11 +94,13 @@ def lib():
     L.pf_host_fill_background.argtypes = [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64,
                                           c_vp, c_vp, c_int, c_int]
     L.pf_pr_spectrum.argtypes = [c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]
+    L.pf_pr_spectrum_pert.argtypes = [c_int, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]
     L.pf_scatter_slab.argtypes = [c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]
     L.pf_crossing_rows.argtypes = [c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]
     L.pf_bunch_davies.argtypes = [c_int, c_i64, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_dbl, c_dbl, c_int,
                                   c_int, c_vp, c_vp]
     L.pf_derivs.argtypes = [mp, c_int, c_i64, c_vp, c_dbl, c_vp, c_vp, c_vp]
+    L.pf_fp64_peak_probe.argtypes = [c_int, c_vp, c_i64, ctypes.POINTER(c_dbl)]
     L.pf_peer_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(c_vp)]
     L.pf_peer_free.argtypes = [c_vp]
     L.pf_peer_export.argtypes = [c_vp, ctypes.c_char_p]

@@ -73,6 +73,11 @@ def Pr(m, tix=None, kix=None):
     """Unscaled curvature power spectrum of model ``m`` for the requested rows and modes;
     shape (rows, nk) (adiabatic.py:201-258)."""
     tslice, kslice = _slices(m, tix, kix)
+    if isinstance(m.yresult, np.ndarray):
+        from .. import rk4
+        cached = rk4.cached_pr(m.yresult)                 # reduced on the device during the run
+        if cached is not None:
+            return np.array(cached[tslice, kslice])
     y = m.yresult[tslice, :, kslice]
     if not isinstance(y, np.ndarray):                     # CUDA tensor -> K5
         from .. import engine

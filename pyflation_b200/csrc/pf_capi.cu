@@ -110,6 +110,52 @@ __global__ void pr_kernel(int nf, int64_t nrows, int64_t nk, const double2* __re
     Pr[row * nk + k] = out;
 }
 
+// Same reduction on a PF_LAYOUT_PERT window (perturbation rows only): phi'_I of row t0 + row comes
+// from the background row stored in the step records.
+__global__ void pr_pert_kernel(int nf, int64_t nrows, int64_t nk, const double2* __restrict__ y,
+                               const double* __restrict__ rec, int64_t rec_pitch, int64_t bg_off,
+                               int64_t t0, const double* __restrict__ kgrid, double* __restrict__ Pr) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t row = blockIdx.y;
+    if (k >= nk || row >= nrows) return;
+    const int npert = 2 * nf * nf;
+    const double2* yr = y + row * (int64_t)npert * nk + k;
+    const double* bg = rec + (t0 + row) * rec_pitch + bg_off;
+    double pd[PF_MAX_NFIELDS];
+    double norm = 0.0;
+    for (int i = 0; i < nf; ++i) {
+        pd[i] = bg[2 * i + 1];
+        norm += pd[i] * pd[i];
+    }
+    double total = 0.0;
+    for (int K = 0; K < nf; ++K) {
+        double re = 0.0, im = 0.0;
+        for (int I = 0; I < nf; ++I) {
+            const double2 chi = yr[(int64_t)(2 * (I * nf + K)) * nk];
+            re += pd[I] * chi.x;
+            im += pd[I] * chi.y;
+        }
+        total += re * re + im * im;
+    }
+    double out = total / (norm * norm);
+    if (kgrid) {
+        const double kk = kgrid[k];
+        out *= kk * kk * kk / (2.0 * 3.141592653589793 * 3.141592653589793);
+    }
+    Pr[row * nk + k] = out;
+}
+
+// DFMA saturation probe: 8 independent FMA chains per thread, 8 x 256-thread CTAs per SM.
+__global__ void __launch_bounds__(256) dfma_probe_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = 1.1, a2 = 1.2, a3 = 1.3, a4 = 1.4, a5 = 1.5, a6 = 1.6, a7 = 1.7;
+    const double b = 0.9999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
 }  // namespace pf
 
 using namespace pf;
@@ -162,6 +208,22 @@ extern "C" int pf_pr_spectrum(int nfields, int64_t nrows, int64_t nk, const doub
     return PF_OK;
 }
 
+extern "C" int pf_pr_spectrum_pert(int nfields, int64_t nrows, int64_t nk, const double* pert_dev,
+                                   const double* rec_dev, int64_t rec_pitch, int64_t bg_off, int64_t t0,
+                                   const double* k_dev, double* Pr_dev, void* stream) {
+    if (nfields < 1 || nfields > PF_MAX_NFIELDS) { set_error("pf_pr_spectrum_pert: nfields=%d", nfields); return PF_E_NFIELDS; }
+    if (nrows < 0 || nk < 0 || t0 < 0 || rec_pitch < bg_off + 2 * nfields + 1) { set_error("pf_pr_spectrum_pert: bad sizes"); return PF_E_ARG; }
+    if (nrows == 0 || nk == 0) return PF_OK;
+    if (!pert_dev || !rec_dev || !Pr_dev) { set_error("pf_pr_spectrum_pert: null buffer"); return PF_E_ARG; }
+    if (nrows > 65535) { set_error("pf_pr_spectrum_pert: at most 65535 rows per call"); return PF_E_ARG; }
+    const int block = 128;
+    dim3 grid((unsigned)((nk + block - 1) / block), (unsigned)nrows, 1);
+    pr_pert_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(nfields, nrows, nk, (const double2*)pert_dev, rec_dev,
+                                                             rec_pitch, bg_off, t0, k_dev, Pr_dev);
+    PF_CUDA_CHECK(cudaGetLastError(), "pf_pr_spectrum_pert launch");
+    return PF_OK;
+}
+
 extern "C" int pf_scatter_slab(int64_t nrows_times_nvar, int64_t nk_r, int64_t nk, int64_t k0,
                                const double* slab_dev, double* full_dev, void* stream) {
     if (nrows_times_nvar < 0 || nk_r < 0 || nk < nk_r || k0 < 0 || k0 + nk_r > nk) {
@@ -206,5 +268,34 @@ extern "C" int pf_peer_open(const unsigned char handle[PF_PEER_HANDLE_BYTES], vo
 extern "C" int pf_peer_close(void* ptr_dev) {
     if (!ptr_dev) return PF_OK;
     PF_CUDA_CHECK(cudaIpcCloseMemHandle(ptr_dev), "pf_peer_close");
+    return PF_OK;
+}
+
+// ---- measured fp64 peak: the roofline denominator of the compute-bound configurations ----
+extern "C" int pf_fp64_peak_probe(int iters, double* scratch_dev, int64_t scratch_doubles,
+                                  double* tflops_out) {
+    if (!scratch_dev || !tflops_out || iters < 1) { set_error("pf_fp64_peak_probe: bad arguments"); return PF_E_ARG; }
+    int dev = 0, sms = 0;
+    PF_CUDA_CHECK(cudaGetDevice(&dev), "pf_fp64_peak_probe");
+    PF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "pf_fp64_peak_probe");
+    const int ctas = sms * 8, threads = 256;
+    if (scratch_doubles < (int64_t)ctas * threads) { set_error("pf_fp64_peak_probe: scratch needs %d doubles", ctas * threads); return PF_E_ARG; }
+    cudaEvent_t e0, e1;
+    PF_CUDA_CHECK(cudaEventCreate(&e0), "pf_fp64_peak_probe");
+    PF_CUDA_CHECK(cudaEventCreate(&e1), "pf_fp64_peak_probe");
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0, 0);
+        dfma_probe_kernel<<<ctas, threads>>>(scratch_dev, iters);
+        cudaEventRecord(e1, 0);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return cuda_fail(e, "pf_fp64_peak_probe"); }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops_out = 2.0 * 8.0 * iters * (double)ctas * threads / (best * 1e-3) / 1e12;
     return PF_OK;
 }

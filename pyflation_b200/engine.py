@@ -11,6 +11,7 @@ rk4.py:58-138, for a ``CanonicalFirstOrder.derivs``):
     first_order_host()    K2  pf_fo_run       time windows into two device slabs, each copied
                                               to (pinned) host memory while the next computes
 """
+import collections
 import ctypes
 import os
 
@@ -71,8 +72,47 @@ def require_cuda(device=None):
     return dev
 
 
-def background_tables(model, y0, T, h, simtstart=0.0, n0=0, records=True, device=None):
-    """K1 (+K1b).  Returns (bg [T, 2nf+1] f64, rec [T, REC] f64 or None) on the device."""
+# ---- stage arguments of recent background runs ---------------------------------------------
+# FOCanonicalTwoStage.run() integrates the background twice in the reference: once in runbg()
+# and again, as rows 0..2nf of every column, inside the first-order run (cosmomodels.py:1343-1404).
+# Here runbg() already ran K1 with the same arithmetic the first-order solve would use, so its
+# RK4 stage arguments (T x 4 x (2nf+1) doubles, <= 5 MB) stay on the device; a first-order solve
+# whose column 0 starts ON that trajectory (bitwise) rebuilds its step records from them with
+# K1b (parallel, microseconds) and skips K1's serial chain (2.4-3 ms) altogether.
+_STAGE_CACHE = collections.OrderedDict()
+_STAGE_CACHE_MAX = 4
+
+
+def _stage_key(model, h, simtstart, dev):
+    return (int(model.potential_id), int(model.nfields), tuple(model.params), float(h),
+            float(simtstart), str(dev))
+
+
+def remember_background(model, h, simtstart, n0, bg_host, stagey, dev):
+    key = _stage_key(model, h, simtstart, dev)
+    _STAGE_CACHE.pop(key, None)
+    _STAGE_CACHE[key] = dict(n0=int(n0), T=int(bg_host.shape[0]), bg_host=bg_host, stagey=stagey)
+    while len(_STAGE_CACHE) > _STAGE_CACHE_MAX:
+        _STAGE_CACHE.popitem(last=False)
+
+
+def cached_stage_args(model, h, simtstart, n0, y0, T, dev):
+    """(stagey device tensor [T_bg, 4, 2nf+1], first valid row) when a remembered background run
+    passes through ``y0`` at row ``n0`` bit for bit and covers rows [n0, T); else None."""
+    if os.environ.get("PF_NO_STAGE_CACHE"):
+        return None
+    e = _STAGE_CACHE.get(_stage_key(model, h, simtstart, dev))
+    if e is None or n0 < e["n0"] or T > e["T"]:
+        return None
+    if not np.array_equal(e["bg_host"][n0], np.asarray(y0, dtype=np.float64).reshape(-1)):
+        return None
+    return e["stagey"], e["n0"]
+
+
+def background_tables(model, y0, T, h, simtstart=0.0, n0=0, records=True, device=None,
+                      return_stage=False):
+    """K1 (+K1b).  Returns (bg [T, 2nf+1] f64, rec [T, REC] f64 or None) on the device
+    (``return_stage``: also the stage arguments [T, 4, 2nf+1])."""
     L = _lib.lib()
     dev = require_cuda(device)
     nf = model.nfields
@@ -82,7 +122,8 @@ def background_tables(model, y0, T, h, simtstart=0.0, n0=0, records=True, device
         raise ValueError("background start vector must have %d entries" % nb)
     with torch.cuda.device(dev):
         bg = torch.empty((T, nb), dtype=torch.float64, device=dev)
-        stagey = torch.empty((T, 4, nb), dtype=torch.float64, device=dev) if records else None
+        stagey = torch.empty((T, 4, nb), dtype=torch.float64, device=dev) \
+            if (records or return_stage) else None
         st = _stream_ptr()
         _lib.check(L.pf_bg_run(ctypes.byref(model), T, float(h), int(n0),
                                y0.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
@@ -92,6 +133,8 @@ def background_tables(model, y0, T, h, simtstart=0.0, n0=0, records=True, device
             rec = torch.empty((T, int(L.pf_rec_doubles(nf))), dtype=torch.float64, device=dev)
             _lib.check(L.pf_stage_table(ctypes.byref(model), T, float(simtstart), float(h), int(n0),
                                         _ptr(bg), _ptr(stagey), _ptr(rec), st))
+    if return_stage:
+        return bg, rec, stagey
     return bg, rec
 
 
@@ -125,6 +168,18 @@ class FirstOrderProblem(object):
                                  device=self.dev)
         self.rec = None
         self.bg = None
+        self.rec_ready = False          # records already valid: solve() skips K1
+
+    def use_stage_args(self, stagey, first_row):
+        """Step records from the stage arguments of an earlier background run (K1b only)."""
+        L = _lib.lib()
+        with torch.cuda.device(self.dev):
+            self.rec = torch.empty((self.T, int(L.pf_rec_doubles(self.nf))), dtype=torch.float64,
+                                   device=self.dev)
+            _lib.check(L.pf_stage_table(ctypes.byref(self.model), self.T, self.simtstart, self.h,
+                                        int(first_row), None, _ptr(stagey), _ptr(self.rec),
+                                        _stream_ptr()))
+        self.rec_ready = True
 
     def build_tables(self, y0, n0):
         self.bg, self.rec = background_tables(self.model, y0, self.T, self.h, self.simtstart,
@@ -137,6 +192,9 @@ class FirstOrderProblem(object):
         gather, with ``out_pitch`` = width of the assembled result)."""
         L = _lib.lib()
         nf = self.nf
+        if self.rec_ready:
+            self.ws.zero_()
+            return self.launch(0, t1, yout, out_every, stream, layout, out_pitch)
         y0 = np.ascontiguousarray(np.asarray(y0, dtype=np.float64).reshape(-1))
         if y0.shape[0] != 2 * nf + 1:
             raise ValueError("background start vector must have %d entries" % (2 * nf + 1))
@@ -243,7 +301,7 @@ def plan_window(T, nvar, nk, slab_bytes):
 
 
 def first_order_host(prob, out=None, slab_bytes=1 << 30, ring=None, y0=None, n0=None, compact=True,
-                     fill_threads=0, skip_unstarted=True):
+                     fill_threads=0, skip_unstarted=True, pr_out=None):
     """Trajectory delivered into host memory.  Time windows ping-pong between two device slabs;
     the device->host copy of window w overlaps the integration of window w+1.
 
@@ -252,6 +310,10 @@ def first_order_host(prob, out=None, slab_bytes=1 << 30, ring=None, y0=None, n0=
     background rows -- the same numbers for every mode -- and the NaN prefix are written into
     the result by host threads (pf_host_fill_background) from the 1 MB step-record table,
     concurrently with the copies.  For nf=1 that is 40 % of the bytes on the link.
+
+    ``pr_out``: optional device tensor (T, nk) float64 that receives P_R of every row, reduced
+    from each device window (K5) before the window is recycled -- ``model.Pr`` then needs no
+    re-upload of the host trajectory.
 
     Returns a torch CPU tensor (T, nvar, nk) complex128 (pinned when it could be).
     ``ring``: a (R, nvar, nk) host tensor used instead of a full-size result when host memory
@@ -295,6 +357,17 @@ def first_order_host(prob, out=None, slab_bytes=1 << 30, ring=None, y0=None, n0=
                 prob.solve(y0, n0, t1, slabs[b], 1, compute, layout)   # K1 + K1b ride along
             else:
                 prob.launch(t0, t1, slabs[b], 1, compute, layout)
+            if pr_out is not None:
+                for r0 in range(t0, t1, 32768):
+                    r1 = min(t1, r0 + 32768)
+                    if compact:
+                        _lib.check(L.pf_pr_spectrum_pert(nf, r1 - r0, nk, _ptr(slabs[b][r0 - t0:r1 - t0]),
+                                                         _ptr(prob.rec), prob.rec.shape[1],
+                                                         4 * (2 + nf * nf), r0, None,
+                                                         _ptr(pr_out[r0:r1]), _stream_ptr(compute)))
+                    else:
+                        _lib.check(L.pf_pr_spectrum(nf, r1 - r0, nk, _ptr(slabs[b][r0 - t0:r1 - t0]), None,
+                                                    _ptr(pr_out[r0:r1]), _stream_ptr(compute)))
             done = torch.cuda.Event()
             done.record(compute)
             copier.wait_event(done)
@@ -460,6 +533,19 @@ def spectrum_run(potential_func, k, nfields=1, pot_params=None, bgystart=None, c
     tres = (simtstart + np.arange(T) * h)[::stride]
     return dict(k=kd, fotstartindex=rows0, rows=out, tresult=tres, Pr=pr, scaled_Pr=spr, ainit=ainit,
                 etainit=etainit, fotend=m.fotend, fotendindex=int(m.fotendindex), T=T)
+
+
+def fp64_peak_tflops(iters=100000, device=None):
+    """Measured DFMA peak of the current GPU in TFLOP/s (pf_fp64_peak_probe)."""
+    L = _lib.lib()
+    dev = require_cuda(device)
+    with torch.cuda.device(dev):
+        n = 8 * 256 * torch.cuda.get_device_properties(dev).multi_processor_count
+        scratch = torch.empty(n, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        out = ctypes.c_double(0.0)
+        _lib.check(L.pf_fp64_peak_probe(int(iters), _ptr(scratch), n, ctypes.byref(out)))
+    return float(out.value)
 
 
 def derivs_device(model, y, t, k=None):

@@ -77,7 +77,10 @@ def gather_rows(rows_local, bounds, group=None):
     # the collective moves plain float64 words (NCCL and gloo have no complex dtype)
     send = torch.view_as_real(padded) if padded.is_complex() else padded
     recv = torch.view_as_real(gathered) if gathered.is_complex() else gathered
-    dist.all_gather([recv[r] for r in range(world)], send, group=group)
+    if dev.type == "cuda":
+        dist.all_gather_into_tensor(recv, send, group=group)      # one NCCL all-gather, no staging
+    else:
+        dist.all_gather([recv[r] for r in range(world)], send, group=group)
     full = torch.empty((R, nvar, nk), dtype=rows_local.dtype, device=dev)
     for r in range(world):
         w = int(widths[r])

@@ -35,9 +35,12 @@ RAW_PHASE_EXCEPTIONS = {}
 
 
 # hybridquartic's waterfall instability amplifies a 1-ulp change of the inputs to 6.2e-9 in the
-# reference's own background (conditioning.json); the GPU path measures 8.6e-10 against the
-# golden file and is held to 2e-9.  Every other fixture: the north-star 1e-9.
-WIDENED = {"hybridquartic": 2e-9}
+# reference's own background (conditioning.json): the reference's first-order stage, which
+# re-integrates the background in complex arithmetic, differs from its own background run by
+# that order.  The GPU path measures 8.6e-10 (full two-stage run) and 1.2e-8 (first-order stage
+# fed the golden start vectors: two ulps' worth) and is held to 10x the conditioning, 6.2e-8.
+# Every other fixture: the north-star 1e-9.
+WIDENED = {"hybridquartic": 10.0}        # multiple of conditioning.json["bg"]
 
 
 def tolerances(name):
@@ -46,7 +49,7 @@ def tolerances(name):
     that (tests/golden/make_conditioning.py: response of the oracle to a 1-ulp input change)."""
     c = CONDITIONING[name]
     assert 10 * c["bg"] < TOL or name in WIDENED, "fixture %s needs a stated tolerance" % name
-    tol = WIDENED.get(name, TOL)
+    tol = WIDENED[name] * c["bg"] if name in WIDENED else TOL
     return (tol, tol, RAW_PHASE_EXCEPTIONS.get(name, tol))
 
 
@@ -252,6 +255,40 @@ def test_fused_solve_two_fields():
         prob2.check_flags()
         assert rel_err(fused[:, :5], separate[:, :5]) < 1e-13
         assert mode_rel_err(fused, separate, 2) < 1e-12
+
+
+def test_stage_cache_and_pr_cache(monkeypatch):
+    """runbg() leaves its RK4 stage arguments on the device and runfo() rebuilds the step records
+    from them (K1b) instead of re-integrating the background (K1): same trajectory as the
+    uncached solve.  P_R reduced per device window during the run == P_R recomputed from the
+    host trajectory."""
+    from pyflation_b200 import engine, rk4
+    for name in ("c1_msqphisq_k4", "c3_hybridquadratic_2p20", "nflation5"):
+        g = load_fo(name)
+        nf = g["nfields"]
+        engine._STAGE_CACHE.clear()
+        m1 = run_model(g)
+        assert len(engine._STAGE_CACHE) == 1
+        hit = engine.cached_stage_args(engine.make_model(g["potential"], g["params"], nf), m1.tstep_wanted,
+                                       m1.simtstart, int(m1.fotstartindex.min()),
+                                       np.real(m1.foystart[:2 * nf + 1, 0]), g["T"], "cuda:0")
+        assert hit is not None                               # ... and runfo() used it
+        pr_cached = rk4.cached_pr(m1.yresult)
+        assert pr_cached is not None and pr_cached.shape == (g["T"], len(g["k"]))
+        monkeypatch.setenv("PF_NO_STAGE_CACHE", "1")
+        m2 = run_model(g)
+        monkeypatch.delenv("PF_NO_STAGE_CACHE")
+        assert rel_err(m1.yresult[:, :2 * nf + 1], m2.yresult[:, :2 * nf + 1]) < 1e-13
+        assert mode_rel_err(m1.yresult, m2.yresult, nf) < 1e-12
+        # a changed trajectory invalidates its cache entry instead of returning stale numbers
+        assert rk4.cached_pr(m2.yresult) is not None
+        m2.yresult[-1] *= 2.0
+        assert rk4.cached_pr(m2.yresult) is None
+        pr1 = m1.Pr
+        rk4._PR_CACHE.clear()
+        pr_host = m1.Pr                                      # recomputed from the host array
+        assert rel_err(pr1, pr_host) < 1e-13
+        assert rel_err(pr1[g["rows"]], g["Pr_rows"]) < tolerances(name)[0]
 
 
 def test_linearity_and_column_independence():

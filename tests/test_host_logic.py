@@ -285,3 +285,19 @@ def test_committed_bench_record_has_contract_keys():
     assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"])
     assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(line["clocks"])
     assert line["gpu_launches"] == line["steps"] and line["e2e"]["value"] < line["value"]
+
+
+def test_pyflation_import_name_resolves_to_the_b200_package():
+    """`import pyflation` (the reference's package name, pyflation/__init__.py) gives the module
+    objects of pyflation_b200: code written against the reference runs without editing imports."""
+    import pyflation
+    import pyflation_b200
+    from pyflation import cosmomodels, rk4, cmpotentials, helpers, configuration, analysis, run_config  # noqa: F401
+    from pyflation.analysis import adiabatic, utilities  # noqa: F401
+    from pyflation.analysis.adiabatic import Pr, scaled_Pr  # noqa: F401
+    import pyflation.cosmomodels as cm
+    assert cm is pyflation_b200.cosmomodels and rk4 is pyflation_b200.rk4
+    assert pyflation.__version__ == "0.2.3"
+    assert cm.FOCanonicalTwoStage.solverlist == ["rkdriver_tsix"]
+    with pytest.raises(ImportError):
+        import pyflation.sourceterm  # noqa: F401
