@@ -36,7 +36,9 @@ extern "C" {
 #endif
 
 #define PF_ABI_VERSION 2
-#define PF_MAX_NFIELDS 8          /* compiled instantiations: nf = 1..8 */
+#define PF_MAX_NFIELDS 8          /* compiled instantiations (state in registers): nf = 1..8 */
+#define PF_MAX_NFIELDS_RT 64      /* runtime-nf kernels: nflation, the one potential of the reference
+                                     defined for any nfields (cmpotentials.py:791-846), nf = 9..64 */
 #define PF_MAX_PARAMS 8
 
 /* potential ids, in the order of pyflation/cmpotentials.py */
@@ -66,7 +68,7 @@ enum pf_error {
     PF_OK = 0,
     PF_E_ARG = -1,            /* null pointer / negative size / bad window */
     PF_E_POTENTIAL = -2,      /* unknown potential id, or nfields not valid for it */
-    PF_E_NFIELDS = -3,        /* nfields outside 1..PF_MAX_NFIELDS */
+    PF_E_NFIELDS = -3,        /* nfields outside 1..PF_MAX_NFIELDS (nflation: 1..PF_MAX_NFIELDS_RT) */
     PF_E_STEP = -4,           /* h is NaN or zero   (rk4.py:63 "Need to specify h.") */
     PF_E_START = -5           /* start index outside the step range (rk4.py:74) */
 };
@@ -116,6 +118,7 @@ int pf_derivs(const pf_model *m, int first_order, int64_t ncol, const double *y_
 int64_t pf_number_of_steps(double simtstart, double tend, double h);  /* rk4.py:73 */
 int64_t pf_nvar(int nfields);                      /* 2 nf^2 + 2 nf + 1 */
 int64_t pf_rec_doubles(int nfields);               /* doubles per step record (below) */
+int64_t pf_rec_bg_offset(int nfields);             /* column of the background row inside a record */
 
 /* ---- K1: background RK4 (replaces rkdriver_tsix + CanonicalBackground.derivs) ----
  * Integrates the real background y = (phi_i, phi'_i, H) from row n0 (state y0_host) to row
@@ -128,8 +131,13 @@ int pf_bg_run(const pf_model *m, int64_t T, double h, int64_t n0, const double *
  * rec_dev[T][pf_rec_doubles(nf)]:  for each RK4 stage s=0..3 of the step n -> n+1:
  * A = U/H^2,  R = 1/(a H),  C[i][l] = (V_il + phi'_i V_l + V_i phi'_l + phi'_i phi'_l U)/H^2
  * (cosmomodels.py:663-674), a = ainit exp(t_stage), t_stage = simtstart + n h (+ h/2, + h/2,
- * + h) (rk4.py:27-55,116-118); then the bg row n (2nf+1 doubles); padded to an even length.
- * Rows n < n0 are NaN. */
+ * + h) (rk4.py:27-55,116-118); then the bg row n (2nf+1 doubles, at column
+ * pf_rec_bg_offset(nf)); padded to an even length.  Rows n < n0 are NaN.
+ * nflation with nf >= 5 stores the factors of C instead of the dense matrix -- its Hessian is
+ * m^2 I (cmpotentials.py:840), so C = d I + (p g^T + g p^T + U p p^T)/H^2 with p = phi',
+ * g = dU: a stage slot is (A, R, d = m^2/H^2, U, 1/H^2, 0, p[nf], g[nf]), and the mode kernel
+ * needs 4 nf + 3 multiply-adds per column for the coupling instead of nf^2.  The records are an
+ * opaque contract between pf_stage_table and pf_fo_run of the same library build. */
 int pf_stage_table(const pf_model *m, int64_t T, double simtstart, double h, int64_t n0,
                    const double *bg_dev, const double *stagey_dev, double *rec_dev,
                    void *stream);

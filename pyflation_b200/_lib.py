@@ -10,7 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # PYFLATION_B200_LIB selects an alternative build of the same ABI (kernel tuning experiments)
 LIB_PATH = os.environ.get("PYFLATION_B200_LIB", os.path.join(_HERE, "lib", "libpyflation_b200.so"))
 
-PF_MAX_NFIELDS = 8
+PF_MAX_NFIELDS = 8            # compiled instantiations
+PF_MAX_NFIELDS_RT = 64        # runtime-nf kernels (nflation)
 PF_MAX_PARAMS = 8
 PF_FLAG_BG_MISMATCH = 1
 PF_LAYOUT_FULL, PF_LAYOUT_PERT = 0, 1
@@ -21,7 +22,7 @@ EXPORTS = [
     "pf_version", "pf_last_error", "pf_potential_id", "pf_potential_name",
     "pf_potential_nfields", "pf_potential_nparams", "pf_potential_param_name",
     "pf_potential_param_default", "pf_potential_eval", "pf_number_of_steps", "pf_nvar",
-    "pf_rec_doubles", "pf_bg_run", "pf_stage_table", "pf_fo_run", "pf_solve_scratch_doubles",
+    "pf_rec_doubles", "pf_rec_bg_offset", "pf_bg_run", "pf_stage_table", "pf_fo_run", "pf_solve_scratch_doubles",
     "pf_fo_solve", "pf_pr_spectrum", "pf_pr_spectrum_pert", "pf_scatter_slab", "pf_copy_rows_d2h",
     "pf_host_fill_background", "pf_crossing_rows", "pf_bunch_davies", "pf_derivs",
     "pf_fp64_peak_probe", "pf_peer_alloc", "pf_peer_free", "pf_peer_export", "pf_peer_open", "pf_peer_close",
@@ -81,6 +82,8 @@ def lib():
     L.pf_nvar.restype = c_i64
     L.pf_rec_doubles.argtypes = [c_int]
     L.pf_rec_doubles.restype = c_i64
+    L.pf_rec_bg_offset.argtypes = [c_int]
+    L.pf_rec_bg_offset.restype = c_i64
     L.pf_bg_run.argtypes = [mp, c_i64, c_dbl, c_i64, ctypes.POINTER(c_dbl), c_vp, c_vp, c_vp]
     L.pf_stage_table.argtypes = [mp, c_i64, c_dbl, c_dbl, c_i64, c_vp, c_vp, c_vp, c_vp]
     L.pf_fo_run.argtypes = [mp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_dbl, c_i64, c_i64,

@@ -58,6 +58,18 @@ def _pr_on_device(y, nfields, chunk_bytes=512 << 20):
     return out
 
 
+def _to_host(block):
+    """Device block -> fresh NumPy array through a page-locked staging tensor (torch's caching
+    pinned allocator makes repeated calls cheap; the array keeps the staging block alive)."""
+    import torch
+    try:
+        host = torch.empty(block.shape, dtype=block.dtype, pin_memory=True)
+    except RuntimeError:
+        host = torch.empty(block.shape, dtype=block.dtype)
+    host.copy_(block)
+    return host.numpy()
+
+
 def _slices(m, tix, kix):
     if tix is None:
         tslice = slice(None)
@@ -77,7 +89,7 @@ def Pr(m, tix=None, kix=None):
         from .. import rk4
         cached = rk4.cached_pr(m.yresult)                 # reduced on the device during the run
         if cached is not None:
-            return np.array(cached[tslice, kslice])
+            return _to_host(cached[tslice, kslice])
     y = m.yresult[tslice, :, kslice]
     if not isinstance(y, np.ndarray):                     # CUDA tensor -> K5
         from .. import engine

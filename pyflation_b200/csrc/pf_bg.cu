@@ -195,6 +195,7 @@ extern "C" int pf_bg_run(const pf_model* m, int64_t T, double h, int64_t n0, con
     if (!y0_host || !bg_dev || T < 1) { set_error("pf_bg_run: null buffer or T < 1"); return PF_E_ARG; }
     if (!(h == h) || h == 0.0) { set_error("pf_bg_run: Need to specify h."); return PF_E_STEP; }
     if (n0 < 0 || n0 > T) { set_error("pf_bg_run: Start times outside range of steps."); return PF_E_START; }
+    if (m->nfields > PF_MAX_NFIELDS) return rt_bg_run(m, T, h, n0, y0_host, bg_dev, stagey_dev, (cudaStream_t)stream);
     BgState y0;
     for (int c = 0; c < 2 * PF_MAX_NFIELDS + 1; ++c) y0.v[c] = c < 2 * m->nfields + 1 ? y0_host[c] : 0.0;
     PotParams par = pack_params(m);
@@ -216,6 +217,7 @@ extern "C" int pf_stage_table(const pf_model* m, int64_t T, double simtstart, do
     if (!stagey_dev || !rec_dev || T < 1) { set_error("pf_stage_table: null buffer or T < 1"); return PF_E_ARG; }
     if (!(h == h) || h == 0.0) { set_error("pf_stage_table: Need to specify h."); return PF_E_STEP; }
     if (n0 < 0 || n0 > T) { set_error("pf_stage_table: Start times outside range of steps."); return PF_E_START; }
+    if (m->nfields > PF_MAX_NFIELDS) return rt_stage_table(m, T, simtstart, h, n0, stagey_dev, rec_dev, (cudaStream_t)stream);
     PotParams par = pack_params(m);
     cudaStream_t st = (cudaStream_t)stream;
     const int block = 128;
@@ -236,6 +238,7 @@ extern "C" int pf_potential_eval(const pf_model* m, int64_t n, const double* y_d
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!y_dev || !U_dev || !dU_dev))) { set_error("pf_potential_eval: null buffer"); return PF_E_ARG; }
     if (n == 0) return PF_OK;
+    if (m->nfields > PF_MAX_NFIELDS) return rt_potential_eval(m, n, y_dev, U_dev, dU_dev, d2U_dev, (cudaStream_t)stream);
     PotParams par = pack_params(m);
     cudaStream_t st = (cudaStream_t)stream;
     const int block = 128;
@@ -256,6 +259,7 @@ extern "C" int pf_derivs(const pf_model* m, int first_order, int64_t ncol, const
     if (ncol < 0) { set_error("pf_derivs: negative size"); return PF_E_ARG; }
     if (ncol == 0) return PF_OK;
     if (!y_dev || !dydx_dev || (first_order && !k_dev)) { set_error("pf_derivs: null buffer"); return PF_E_ARG; }
+    if (m->nfields > PF_MAX_NFIELDS) return rt_derivs(m, first_order, ncol, y_dev, t, k_dev, dydx_dev, (cudaStream_t)stream);
     PotParams par = pack_params(m);
     cudaStream_t st = (cudaStream_t)stream;
     const int block = 64;

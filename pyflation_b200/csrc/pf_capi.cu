@@ -58,8 +58,9 @@ int check_model(const pf_model* m) {
         set_error("unknown potential id %d", m->potential_id);
         return PF_E_POTENTIAL;
     }
-    if (m->nfields < 1 || m->nfields > PF_MAX_NFIELDS) {
-        set_error("nfields=%d outside 1..%d", m->nfields, PF_MAX_NFIELDS);
+    const int nf_max = m->potential_id == PF_NFLATION ? PF_MAX_NFIELDS_RT : PF_MAX_NFIELDS;
+    if (m->nfields < 1 || m->nfields > nf_max) {
+        set_error("nfields=%d outside 1..%d", m->nfields, nf_max);
         return PF_E_NFIELDS;
     }
     const int want = kPot[m->potential_id].nfields;
@@ -73,6 +74,7 @@ int check_model(const pf_model* m) {
 
 int rec_kind(const pf_model* m) {
     static const bool dense_only = getenv("PF_FO_DENSE") != nullptr;
+    if (m->nfields > PF_MAX_NFIELDS) return PF_REC_FACTORED;       // runtime-nf kernels: factored only
     return (!dense_only && m->potential_id == PF_NFLATION && m->nfields >= 5) ? PF_REC_FACTORED
                                                                               : PF_REC_DENSE;
 }
@@ -86,7 +88,7 @@ __global__ void pr_kernel(int nf, int64_t nrows, int64_t nk, const double2* __re
     if (k >= nk || row >= nrows) return;
     const int nvar = nvar_of(nf), nb = nbg_of(nf);
     const double2* yr = y + row * (int64_t)nvar * nk + k;
-    double pd[PF_MAX_NFIELDS];
+    double pd[PF_MAX_NFIELDS_RT];
     double norm = 0.0;
     for (int i = 0; i < nf; ++i) {
         pd[i] = yr[(int64_t)(2 * i + 1) * nk].x;          // adiabatic.py:253 keeps the real part
@@ -121,7 +123,7 @@ __global__ void pr_pert_kernel(int nf, int64_t nrows, int64_t nk, const double2*
     const int npert = 2 * nf * nf;
     const double2* yr = y + row * (int64_t)npert * nk + k;
     const double* bg = rec + (t0 + row) * rec_pitch + bg_off;
-    double pd[PF_MAX_NFIELDS];
+    double pd[PF_MAX_NFIELDS_RT];
     double norm = 0.0;
     for (int i = 0; i < nf; ++i) {
         pd[i] = bg[2 * i + 1];
@@ -193,10 +195,11 @@ extern "C" int64_t pf_number_of_steps(double simtstart, double tend, double h) {
 }
 extern "C" int64_t pf_nvar(int nfields) { return nvar_of(nfields); }
 extern "C" int64_t pf_rec_doubles(int nfields) { return rec_of(nfields); }
+extern "C" int64_t pf_rec_bg_offset(int nfields) { return rec_bg_offset(nfields); }
 
 extern "C" int pf_pr_spectrum(int nfields, int64_t nrows, int64_t nk, const double* y_dev,
                               const double* k_dev, double* Pr_dev, void* stream) {
-    if (nfields < 1 || nfields > PF_MAX_NFIELDS) { set_error("pf_pr_spectrum: nfields=%d", nfields); return PF_E_NFIELDS; }
+    if (nfields < 1 || nfields > PF_MAX_NFIELDS_RT) { set_error("pf_pr_spectrum: nfields=%d", nfields); return PF_E_NFIELDS; }
     if (nrows < 0 || nk < 0) { set_error("pf_pr_spectrum: negative size"); return PF_E_ARG; }
     if (nrows == 0 || nk == 0) return PF_OK;
     if (!y_dev || !Pr_dev) { set_error("pf_pr_spectrum: null buffer"); return PF_E_ARG; }
@@ -211,7 +214,7 @@ extern "C" int pf_pr_spectrum(int nfields, int64_t nrows, int64_t nk, const doub
 extern "C" int pf_pr_spectrum_pert(int nfields, int64_t nrows, int64_t nk, const double* pert_dev,
                                    const double* rec_dev, int64_t rec_pitch, int64_t bg_off, int64_t t0,
                                    const double* k_dev, double* Pr_dev, void* stream) {
-    if (nfields < 1 || nfields > PF_MAX_NFIELDS) { set_error("pf_pr_spectrum_pert: nfields=%d", nfields); return PF_E_NFIELDS; }
+    if (nfields < 1 || nfields > PF_MAX_NFIELDS_RT) { set_error("pf_pr_spectrum_pert: nfields=%d", nfields); return PF_E_NFIELDS; }
     if (nrows < 0 || nk < 0 || t0 < 0 || rec_pitch < bg_off + 2 * nfields + 1) { set_error("pf_pr_spectrum_pert: bad sizes"); return PF_E_ARG; }
     if (nrows == 0 || nk == 0) return PF_OK;
     if (!pert_dev || !rec_dev || !Pr_dev) { set_error("pf_pr_spectrum_pert: null buffer"); return PF_E_ARG; }

@@ -20,9 +20,16 @@ int cuda_fail(cudaError_t e, const char* where);
 
 __host__ __device__ constexpr int nvar_of(int nf) { return 2 * nf * nf + 2 * nf + 1; }
 __host__ __device__ constexpr int nbg_of(int nf) { return 2 * nf + 1; }
-// record = bg row (2nf+1) + 4 stages x (A, R, C[nf][nf]), padded to an even number of doubles
+// record = 4 stage slots + bg row (2nf+1), padded to an even number of doubles.  A slot holds
+// (A, R, C[nf][nf]) for the compiled instantiations (nf <= PF_MAX_NFIELDS; the factored nflation
+// records of nf >= 5 use a prefix of it), and (A, R, d, U, 1/H^2, 0, p[nf], g[nf]) for the
+// runtime-nf kernels above that (pf_rt.cu).
+__host__ __device__ constexpr int rec_stage_width(int nf) {
+    return nf <= PF_MAX_NFIELDS ? 2 + nf * nf : 6 + 2 * nf;
+}
+__host__ __device__ constexpr int rec_bg_offset(int nf) { return 4 * rec_stage_width(nf); }
 __host__ __device__ constexpr int rec_of(int nf) {
-    return ((2 * nf + 1 + 4 * (2 + nf * nf)) + 1) & ~1;
+    return ((2 * nf + 1 + 4 * rec_stage_width(nf)) + 1) & ~1;
 }
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }

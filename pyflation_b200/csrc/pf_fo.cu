@@ -75,6 +75,7 @@ extern "C" int pf_fo_run(const pf_model* m, int64_t nk, const double* k_dev, con
     cudaStream_t st = (cudaStream_t)stream;
     static const bool generic_only = getenv("PF_FO_GENERIC") != nullptr;
     const bool fact = rec_kind(m) == PF_REC_FACTORED;   // must match the records pf_stage_table wrote
+    if (m->nfields > PF_MAX_NFIELDS) return rt_fo_run(m, a, st);
     switch (m->nfields) {
         case 1:
             if (!generic_only) launch_fo1(a, st);                     // single-field fast path
@@ -94,7 +95,7 @@ extern "C" int pf_fo_run(const pf_model* m, int64_t nk, const double* k_dev, con
 }
 
 extern "C" int64_t pf_solve_scratch_doubles(int nfields, int64_t T) {
-    if (nfields < 1 || nfields > PF_MAX_NFIELDS || T < 0) return -1;
+    if (nfields < 1 || nfields > PF_MAX_NFIELDS_RT || T < 0) return -1;
     return T * (int64_t)(rec_of(nfields) + 5 * nbg_of(nfields));
 }
 

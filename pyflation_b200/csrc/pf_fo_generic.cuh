@@ -236,10 +236,12 @@ __device__ __forceinline__ void rk4_step_factored(const double* __restrict__ r, 
 #ifndef PF_FO_MINB
 #define PF_FO_MINB(NF) ((NF) >= 5 ? 3 : 1)
 #endif
-// factored records: six state arrays (96 registers at nf = 8) and no kv array -> 128 registers,
-// four 128-thread CTAs per SM
+// factored records: six state arrays (96 registers at nf = 8) and no kv array.  Measured at nf = 8:
+// three CTAs per SM (165 registers, no spills) 2.50e9 mode-steps/s, four (128 registers, 228 B of
+// spills) 1.97e9 -- A/B switch PF_FO_FACT_MINB
+
 #ifndef PF_FO_MINB_FACT
-#define PF_FO_MINB_FACT 4
+#define PF_FO_MINB_FACT 3
 #endif
 // Consumer: integrates column j of the mode matrix for the k tile bx.  `progress` (may be null)
 // is the producer's published record count in fused launches (pf_fused.cu).

@@ -74,6 +74,17 @@ int launch_fo1(const FoArgs& a, cudaStream_t st);   // pf_fo1.cu
 bool launch_fo_fused_generic(const pf_model* m, const FoArgs& a, double simtstart, int64_t n0,
                              const double* y0_host, double* rec, double* stagey, int32_t* ws,
                              cudaStream_t st);   // pf_fused.cu (nf = 2)
+// runtime-nf path (pf_rt.cu): nflation with PF_MAX_NFIELDS < nfields <= PF_MAX_NFIELDS_RT
+int rt_bg_run(const pf_model* m, int64_t T, double h, int64_t n0, const double* y0_host, double* bg,
+              double* stagey, cudaStream_t st);
+int rt_stage_table(const pf_model* m, int64_t T, double simtstart, double h, int64_t n0,
+                   const double* stagey, double* rec, cudaStream_t st);
+int rt_fo_run(const pf_model* m, const FoArgs& a, cudaStream_t st);
+int rt_potential_eval(const pf_model* m, int64_t n, const double* y, double* U, double* dU, double* d2U,
+                      cudaStream_t st);
+int rt_derivs(const pf_model* m, int first_order, int64_t ncol, const double* y, double t, const double* k,
+              double* dydx, cudaStream_t st);
+
 bool launch_fo1_fused(const pf_model* m, const FoArgs& a, double simtstart, int64_t n0,
                       const double* y0_host, double* rec, int32_t* ws, cudaStream_t st);
 

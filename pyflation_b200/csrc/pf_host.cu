@@ -42,6 +42,26 @@ static void fill_rows_nb(double* yout, int nvar, int64_t nk, int64_t ta, int64_t
     _mm_sfence();
 }
 
+// any number of background rows (nfields > 8): one row at a time
+static void fill_rows_any(double* yout, int nb, int nvar, int64_t nk, int64_t ta, int64_t tb, const double* bg,
+                          int64_t bg_pitch, int64_t bg_off, const int64_t* tsix, const double* ystart,
+                          bool pert_nan) {
+    const __m128d nan2 = _mm_set1_pd(NAN);
+    const int nan_rows = pert_nan ? nvar : nb;
+    for (int64_t t = ta; t < tb; ++t) {
+        for (int v = 0; v < nan_rows; ++v) {
+            double* row = yout + 2 * ((t * nvar + v) * nk);
+            const __m128d val = _mm_set_pd(0.0, v < nb ? bg[t * bg_pitch + bg_off + v] : 0.0);
+            for (int64_t k = 0; k < nk; ++k) {
+                const int64_t s = tsix[k];
+                if (t < s) _mm_stream_pd(row + 2 * k, nan2);
+                else if (v < nb) _mm_stream_pd(row + 2 * k, t > s ? val : _mm_loadu_pd(ystart + 2 * ((int64_t)v * nk + k)));
+            }
+        }
+    }
+    _mm_sfence();
+}
+
 static void fill_rows(double* yout, int nb, int nvar, int64_t nk, int64_t ta, int64_t tb,
                       const double* bg, int64_t bg_pitch, int64_t bg_off, const int64_t* tsix,
                       const double* ystart, bool pert_nan) {
@@ -49,7 +69,7 @@ static void fill_rows(double* yout, int nb, int nvar, int64_t nk, int64_t ta, in
 #define PF_CASE(N) case N: fill_rows_nb<N>(yout, nvar, nk, ta, tb, bg, bg_pitch, bg_off, tsix, ystart, pert_nan); break;
         PF_CASE(3) PF_CASE(5) PF_CASE(7) PF_CASE(9) PF_CASE(11) PF_CASE(13) PF_CASE(15) PF_CASE(17)
 #undef PF_CASE
-        default: break;
+        default: fill_rows_any(yout, nb, nvar, nk, ta, tb, bg, bg_pitch, bg_off, tsix, ystart, pert_nan); break;
     }
 }
 
@@ -74,7 +94,7 @@ extern "C" int pf_host_fill_background(double* yout_host, int nfields, int64_t n
                                        const double* bg_host, int64_t bg_pitch, int64_t bg_off,
                                        const int64_t* tsix_host, const double* ystart_host, int pert_nan,
                                        int nthreads) {
-    if (nfields < 1 || nfields > PF_MAX_NFIELDS) { set_error("pf_host_fill_background: nfields=%d", nfields); return PF_E_NFIELDS; }
+    if (nfields < 1 || nfields > PF_MAX_NFIELDS_RT) { set_error("pf_host_fill_background: nfields=%d", nfields); return PF_E_NFIELDS; }
     if (nk < 0 || t0 < 0 || t1 < t0) { set_error("pf_host_fill_background: bad sizes"); return PF_E_ARG; }
     if (nk == 0 || t0 == t1) return PF_OK;
     if (!yout_host || !bg_host || !tsix_host || !ystart_host) { set_error("pf_host_fill_background: null buffer"); return PF_E_ARG; }

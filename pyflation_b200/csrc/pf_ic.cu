@@ -87,7 +87,7 @@ extern "C" int pf_bunch_davies(int nfields, int64_t nk, const double* k_dev, con
                                const double* bg_dev, double simtstart, double h, double ainit,
                                double etainit, int phase, int suppress_ix, double* ystart_dev,
                                void* stream) {
-    if (nfields < 1 || nfields > PF_MAX_NFIELDS) { set_error("pf_bunch_davies: nfields=%d", nfields); return PF_E_NFIELDS; }
+    if (nfields < 1 || nfields > PF_MAX_NFIELDS_RT) { set_error("pf_bunch_davies: nfields=%d", nfields); return PF_E_NFIELDS; }
     if (nk < 0) { set_error("pf_bunch_davies: bad sizes"); return PF_E_ARG; }
     if (nk == 0) return PF_OK;
     if (!k_dev || !rows_dev || !bg_dev || !ystart_dev) { set_error("pf_bunch_davies: null buffer"); return PF_E_ARG; }

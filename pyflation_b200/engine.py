@@ -37,9 +37,9 @@ def make_model(potential_func, pot_params, nfields, ainit=1.0):
     if nf_required and nf_required != nfields:
         raise ValueError("potential %s is defined for nfields=%d, not %d"
                          % (potential_func, nf_required, nfields))
-    if not 1 <= nfields <= _lib.PF_MAX_NFIELDS:
-        raise NotImplementedError("nfields=%d: kernels are compiled for 1..%d fields"
-                                  % (nfields, _lib.PF_MAX_NFIELDS))
+    nf_max = _lib.PF_MAX_NFIELDS_RT if potential_func == "nflation" else _lib.PF_MAX_NFIELDS
+    if not 1 <= nfields <= nf_max:
+        raise NotImplementedError("nfields=%d: the kernels take 1..%d fields" % (nfields, nf_max))
     m = PfModel()
     m.potential_id = pid
     m.nfields = nfields
@@ -363,7 +363,7 @@ def first_order_host(prob, out=None, slab_bytes=1 << 30, ring=None, y0=None, n0=
                     if compact:
                         _lib.check(L.pf_pr_spectrum_pert(nf, r1 - r0, nk, _ptr(slabs[b][r0 - t0:r1 - t0]),
                                                          _ptr(prob.rec), prob.rec.shape[1],
-                                                         4 * (2 + nf * nf), r0, None,
+                                                         int(L.pf_rec_bg_offset(nf)), r0, None,
                                                          _ptr(pr_out[r0:r1]), _stream_ptr(compute)))
                     else:
                         _lib.check(L.pf_pr_spectrum(nf, r1 - r0, nk, _ptr(slabs[b][r0 - t0:r1 - t0]), None,
@@ -400,7 +400,7 @@ def first_order_host(prob, out=None, slab_bytes=1 << 30, ring=None, y0=None, n0=
                 # time step while the remaining windows compute and copy
                 rec_host = prob.rec.cpu().numpy()
                 d2h_bytes += rec_host.nbytes
-                bg_off = 4 * (2 + nf * nf)
+                bg_off = int(L.pf_rec_bg_offset(nf))
                 # share the host cores between the ranks of one box (torchrun sets LOCAL_WORLD_SIZE)
                 local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
                 nthreads = fill_threads or max(1, len(os.sched_getaffinity(0)) // local_world)

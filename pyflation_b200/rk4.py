@@ -20,9 +20,11 @@ rk_log = logging.getLogger(__name__)
 last_transfer = {"h2d_bytes": 0, "d2h_bytes": 0}
 
 # P_R(t, k) of recent first-order results, reduced on the device while the trajectory was still
-# there (engine.first_order_host, K5 per window); analysis.Pr looks results up here so that
-# ``model.Pr`` does not upload the host trajectory again.  Keyed by id(yresult); an entry is used
-# only while a fingerprint of the array (sampled entries of the last rows) still matches.
+# there (engine.first_order_host, K5 per window) and KEPT on the device (T*nk*8 bytes, at most
+# PR_CACHE_BYTES each, two entries); analysis.Pr looks results up here, so ``model.Pr`` neither
+# uploads the host trajectory again nor pays for rows nobody asked for: only the requested
+# (rows, k) block crosses PCIe.  Keyed by id(yresult); an entry is used only while a fingerprint
+# of the array (sampled entries of the last rows) still matches.
 _PR_CACHE = {}
 _PR_CACHE_MAX = 2
 PR_CACHE_BYTES = 1 << 30            # cache P_R when T*nk*8 is at most this
@@ -34,7 +36,7 @@ def _fingerprint(y):
 
 
 def cached_pr(yresult):
-    """P_R rows (T, nk) float64 (read-only) cached for this very array, or None."""
+    """P_R rows as a CUDA tensor (T, nk) float64 cached for this very array, or None."""
     e = _PR_CACHE.get(id(yresult))
     if e is None or e[0] != yresult.shape:
         return None
@@ -45,7 +47,6 @@ def cached_pr(yresult):
 
 
 def _remember_pr(yresult, pr):
-    pr.flags.writeable = False
     _PR_CACHE[id(yresult)] = (yresult.shape, _fingerprint(yresult), pr)
     while len(_PR_CACHE) > _PR_CACHE_MAX:
         _PR_CACHE.pop(next(iter(_PR_CACHE)))
@@ -191,7 +192,7 @@ def _run_first_order(model, ystart, simtstart, tsix, T, h, yresult_out=None, row
     last_transfer.update(h2d_bytes=prob.h2d_bytes, d2h_bytes=prob.d2h_bytes)
     yarr = yresult_out if (yresult_out is not None and not torch.is_tensor(yresult_out)) else res.numpy()
     if pr_dev is not None:
-        _remember_pr(yarr, pr_dev.cpu().numpy())
+        _remember_pr(yarr, pr_dev)
     return yarr
 
 

@@ -274,7 +274,7 @@ def test_stage_cache_and_pr_cache(monkeypatch):
                                        np.real(m1.foystart[:2 * nf + 1, 0]), g["T"], "cuda:0")
         assert hit is not None                               # ... and runfo() used it
         pr_cached = rk4.cached_pr(m1.yresult)
-        assert pr_cached is not None and pr_cached.shape == (g["T"], len(g["k"]))
+        assert pr_cached is not None and tuple(pr_cached.shape) == (g["T"], len(g["k"])) and pr_cached.is_cuda
         monkeypatch.setenv("PF_NO_STAGE_CACHE", "1")
         m2 = run_model(g)
         monkeypatch.delenv("PF_NO_STAGE_CACHE")
