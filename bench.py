@@ -347,6 +347,67 @@ def measure_extra_configs(hbm_peak, fp64_peak, reps=3, device_index=0):
     return out_list
 
 
+def measure_window_config(hbm_peak, fp64_peak, reps=3, device_index=0):
+    """configs[3] as a windowed full-trajectory run sees it: nflation nf=8, all 2^18 modes, every
+    row of a 128-row time window written (78 GB), state carried in from the rows before.  This is
+    the pattern engine.first_order_host uses for trajectories that fit nowhere at once, and it
+    fills the GPU evenly (the 2^13-mode full run is 2.3 waves of CTAs)."""
+    import torch
+    from pyflation_b200 import cosmomodels, engine
+    name = "configs[3] nflation nf=8, 2^18 modes, rows [4096, 4224) of a windowed full trajectory (78 GB)"
+    try:
+        nf, nk, t0w, t1w = 8, 2 ** 18, 4096, 4224
+        k = np.linspace(KMIN, KMAX, nk)
+        m = cosmomodels.FOCanonicalTwoStage(k=k, potential_func="nflation", pot_params={"nfields": nf},
+                                            nfields=nf, bgystart=None, cq=CQ, tend=TEND, tstep_wanted=H)
+        m.runbg()
+        m.setfoics()
+        T = int(np.around(m.fotend / H) + 1)
+        assert int(m.fotstartindex.max()) < t0w
+        pm = engine.make_model("nflation", {"nfields": nf}, nf, m.ainit)
+        prob = engine.FirstOrderProblem(pm, k, m.fotstartindex, m.foystart, 0.0, T, H)
+        prob.build_tables(np.real(m.foystart[0:2 * nf + 1, 0]).copy(), int(m.fotstartindex.min()))
+        prob.launch(0, t0w, None, 0)                          # state at row t0w
+        state0 = prob.state.clone()
+        out = torch.empty((t1w - t0w, prob.nvar, nk), dtype=torch.complex128, device="cuda")
+        prob.launch(t0w, t1w, out, 1)
+        torch.cuda.synchronize()
+        sampler = ClockSampler(device_index)
+        sampler.start()
+        ev = _events(reps)
+        for a, b in ev:
+            prob.state.copy_(state0)
+            a.record()
+            prob.launch(t0w, t1w, out, 1)
+            b.record()
+        torch.cuda.synchronize()
+        sampler.stop_flag = True
+        sampler.join()
+        prob.check_flags()
+        ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+        assert bool(torch.isfinite(torch.view_as_real(out[-1])).all())
+        mode_steps = float((t1w - t0w) * nk)
+        alg_bytes = mode_steps * 16 * prob.nvar
+        flops = mode_steps * FLOPS_PER_MODE_STEP[nf]
+        f_hbm = alg_bytes / (ms * 1e-3) / 1e9 / hbm_peak
+        f_fp = flops / (ms * 1e-3) / 1e12 / fp64_peak
+        del out, prob, state0
+        torch.cuda.empty_cache()
+        return {"workload": name, "nk": nk, "T": T, "window": [t0w, t1w], "value": mode_steps / (ms * 1e-3),
+                "ms": ms, "mode_kernel_ms": ms, "mode_kernel_value": mode_steps / (ms * 1e-3),
+                "output_policy": "every row of the window", "clocks": sampler.result(),
+                "roofline": {"bound": "hbm" if f_hbm >= f_fp else "fp64", "frac": max(f_hbm, f_fp),
+                             "timed": "mode kernel",
+                             "hbm": {"achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": f_hbm},
+                             "fp64": {"achieved": flops / (ms * 1e-3) / 1e12, "peak": fp64_peak,
+                                      "unit": "TFLOP/s", "frac": f_fp,
+                                      "flops_per_mode_step": FLOPS_PER_MODE_STEP[nf]}}}
+    except Exception as err:
+        torch.cuda.empty_cache()
+        return {"workload": name, "error": repr(err)}
+
+
 def measure_config5(world, rank, barrier):
     """BASELINE configs[4]: msqphisq, k-sharded, device-resident pipeline.
     strong        : fixed 2^24-mode grid over the N ranks, P_R(k) gathered with NCCL.
@@ -594,6 +655,7 @@ def run_gpu_arm(args):
         extras["fp64_peak_tflops"] = fp64_peak
         if world == 1:
             extras["configs"] = measure_extra_configs(peak, fp64_peak, device_index=local_rank)
+            extras["configs"].append(measure_window_config(peak, fp64_peak, device_index=local_rank))
         extras.update(measure_config5(world, rank, barrier))
         if world > 1:
             extras["collective"] = measure_collective(world, rank, barrier)

@@ -90,6 +90,8 @@ typedef struct pf_model {
 
 /* flags written by pf_fo_run into *flags_dev (bitwise OR) */
 #define PF_FLAG_BG_MISMATCH 1   /* a column's ystart background rows are not on column 0's trajectory */
+#define PF_FLAG_TIMEOUT 2       /* a fused launch gave up waiting for its producer / lock-step partners
+                                   (~20 s); the result is invalid -- rerun with PF_FO_NOFUSE=1 */
 
 int pf_version(void);
 const char *pf_last_error(void);

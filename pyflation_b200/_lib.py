@@ -14,6 +14,7 @@ PF_MAX_NFIELDS = 8            # compiled instantiations
 PF_MAX_NFIELDS_RT = 64        # runtime-nf kernels (nflation)
 PF_MAX_PARAMS = 8
 PF_FLAG_BG_MISMATCH = 1
+PF_FLAG_TIMEOUT = 2
 PF_LAYOUT_FULL, PF_LAYOUT_PERT = 0, 1
 PF_PEER_HANDLE_BYTES = 64
 

@@ -81,6 +81,8 @@ extern "C" int pf_fo_run(const pf_model* m, int64_t nk, const double* k_dev, con
             if (!generic_only) launch_fo1(a, st);                     // single-field fast path
             else launch_fo<1, 2>(a, st);
             break;
+        // nf = 2: thread = (k, j), complex.  A (k, j, re|im) split for strided launches (half the
+        // registers, up to 8 CTAs per SM) measured 15-22 % slower on B200 (profiles/r2_ab_*).
         case 2: launch_fo<2, 2>(a, st); break;
         case 3: launch_fo<3, 1>(a, st); break;
         case 4: launch_fo<4, 1>(a, st); break;

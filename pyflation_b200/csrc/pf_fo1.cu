@@ -87,6 +87,7 @@ struct LockStep {
     int* counter;                                     // null: no lock-step
     int nconsumers;
     int rows;                                         // barrier period
+    int32_t* flags;                                   // PF_FLAG_TIMEOUT goes here
 };
 
 __device__ __forceinline__ void lockstep_barrier(const LockStep& ls, int64_t row) {
@@ -100,7 +101,10 @@ __device__ __forceinline__ void lockstep_barrier(const LockStep& ls, int64_t row
             asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(have) : "l"(ls.counter) : "memory");
             if (have >= target) break;
             __nanosleep(64);
-            if (++spins > (1u << 27)) __trap();
+            if (++spins > PF_SPIN_LIMIT) {
+                if (ls.flags) atomicOr(ls.flags, PF_FLAG_TIMEOUT);
+                break;
+            }
         }
     }
     __syncthreads();
@@ -115,7 +119,7 @@ struct Fo1Smem {                                      // one per CTA, owned by t
 template <bool PERT>
 __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nthreads,
                                             const long long* progress, Fo1Smem& sm,
-                                            const LockStep ls = LockStep{nullptr, 0, FO1_LOCKSTEP_ROWS}) {
+                                            const LockStep ls = LockStep{nullptr, 0, FO1_LOCKSTEP_ROWS, nullptr}) {
     constexpr int NV = PERT ? 2 : 5;                  // rows per time step in the output
     constexpr int XO = PERT ? 0 : 3;                  // row of dphi within a time step
     double (&srec)[2][FO1_CH * FO1_REC] = sm.srec;
@@ -195,7 +199,7 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
         const int64_t base = c0 + c * FO1_CH;
         const int64_t cnt = (a.t1 - base) < FO1_CH ? (a.t1 - base) : FO1_CH;
         const uint32_t bytes = (uint32_t)(cnt * FO1_REC * sizeof(double));
-        if (progress) wait_progress(progress, base + cnt);
+        if (progress) wait_progress(progress, base + cnt, a.flags);
         mbar_expect_tx(&bars[buf], bytes);
         bulk_g2s(&srec[buf][0], a.rec + base * FO1_REC, bytes, &bars[buf]);
     };
@@ -214,6 +218,26 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
         Coef nxt = load_record(&srec[buf][0]);
         for (int q = 0; q < cnt; ++q) {
             n = base + q;
+            if (n > tsmax && n != next_out && ls.counter == nullptr) {
+                // ---- tight run (strided / state-only launches, which are bound by the fp64 pipe):
+                // every mode of the CTA is running and no row is stored before `lim`, so the steps
+                // up to there are nothing but record loads and RK4 arithmetic -- no output tests,
+                // no register copies of a prefetched record (profiles/r2_c5_*: the general loop
+                // issues 136 instructions per step for 56 fp64 ones)
+                int64_t lim = next_out - base < (int64_t)cnt ? next_out - base : (int64_t)cnt;
+                if (a.T - 1 - base < lim) lim = a.T - 1 - base;
+                if (lim > q) {
+                    const int qe = (int)lim;
+#pragma unroll 2
+                    for (; q < qe; ++q) {
+                        const Coef ct = load_record(&srec[buf][q * FO1_REC]);
+                        rk4_mode(ct, kval, h, hh, h6, x, v);
+                    }
+                    --q;                                  // the for statement steps to qe
+                    if (qe < cnt) nxt = load_record(&srec[buf][qe * FO1_REC]);
+                    continue;
+                }
+            }
             const Coef cf = nxt;
             if (q + 1 < cnt) nxt = load_record(&srec[buf][(q + 1) * FO1_REC]);
             const bool out = (n == next_out);
@@ -328,6 +352,10 @@ __device__ __forceinline__ void fo1_produce(const FoArgs& a, const ProdArgs& f) 
     const int64_t T = a.T, n0 = f.n0;
     long long* progress = reinterpret_cast<long long*>(f.ws + 2);
     if (tid == 0) { s_head = n0; s_tail = n0; }
+    // records of rows before n0 are NaN, exactly as pf_stage_table leaves them: a caller whose
+    // tsix dips below n0 gets NaN trajectories, not uninitialised memory
+    for (int64_t i = tid; i < n0 * FO1_REC; i += PROD_THREADS) f.rec[i] = qnan();
+    __threadfence();
     asm volatile("bar.sync 2, %0;" ::"n"(PROD_THREADS) : "memory");
 
     if (tid < 32) {
@@ -338,7 +366,7 @@ __device__ __forceinline__ void fo1_produce(const FoArgs& a, const ProdArgs& f) 
             if ((n & 7) == 0) {
                 unsigned spins = 0;
                 while (n - s_tail > PROD_RING - 16) {
-                    if (++spins > (1u << 30)) __trap();
+                    if (++spins > (1u << 30)) { atomicOr(f.ws + 1, PF_FLAG_TIMEOUT); break; }
                 }
             }
             double* slot = ring[n % PROD_RING];
@@ -372,7 +400,7 @@ __device__ __forceinline__ void fo1_produce(const FoArgs& a, const ProdArgs& f) 
         {
             unsigned spins = 0;
             while (s_head < need) {
-                if (++spins > (1u << 30)) __trap();
+                if (++spins > (1u << 30)) { atomicOr(f.ws + 1, PF_FLAG_TIMEOUT); break; }
             }
             __threadfence_block();                    // ring reads stay behind the s_head read
         }
@@ -413,7 +441,7 @@ __global__ void __launch_bounds__(512) fo1_fused_kernel(FoArgs a, ProdArgs f, in
     }
     const long long* progress = reinterpret_cast<const long long*>(f.ws + 2);
     __shared__ Fo1Smem sm;
-    const LockStep ls{lockstep ? f.ws + 4 : nullptr, (int)gridDim.x - 1, lockstep > 1 ? lockstep : FO1_LOCKSTEP_ROWS};
+    const LockStep ls{lockstep ? f.ws + 4 : nullptr, (int)gridDim.x - 1, lockstep > 1 ? lockstep : FO1_LOCKSTEP_ROWS, f.ws + 1};
     if (a.layout == PF_LAYOUT_PERT) fo1_consume<true>(a, cta - 1, cthreads, progress, sm, ls);
     else fo1_consume<false>(a, cta - 1, cthreads, progress, sm, ls);
 }

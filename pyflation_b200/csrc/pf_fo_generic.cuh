@@ -231,6 +231,60 @@ __device__ __forceinline__ void rk4_step_factored(const double* __restrict__ r, 
     });
 }
 
+// one classical RK4 step n -> n+1 (rk4.py:27-55) from the dense record r
+template <int NF, int NC>
+__device__ __forceinline__ void rk4_step_dense(const double* __restrict__ r, double kval, double h,
+                                               double hh, double h6, double (&x)[NF][NC],
+                                               double (&v)[NF][NC]) {
+    constexpr int SW = FoShape<NF>::SW;
+    double kv[NF][NC], ax[NF][NC], av[NF][NC], xt[NF][NC], vt[NF][NC];
+    mode_rhs<NF, NC>(r, kval, x, v, kv);
+#pragma unroll
+    for (int i = 0; i < NF; ++i)
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc) {
+            ax[i][cc] = v[i][cc];
+            av[i][cc] = kv[i][cc];
+            xt[i][cc] = fma(hh, v[i][cc], x[i][cc]);
+            vt[i][cc] = fma(hh, kv[i][cc], v[i][cc]);
+        }
+    mode_rhs<NF, NC>(r + SW, kval, xt, vt, kv);
+#pragma unroll
+    for (int i = 0; i < NF; ++i)
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc) {
+            ax[i][cc] = fma(2.0, vt[i][cc], ax[i][cc]);
+            av[i][cc] = fma(2.0, kv[i][cc], av[i][cc]);
+            xt[i][cc] = fma(hh, vt[i][cc], x[i][cc]);
+            vt[i][cc] = fma(hh, kv[i][cc], v[i][cc]);
+        }
+    mode_rhs<NF, NC>(r + 2 * SW, kval, xt, vt, kv);
+#pragma unroll
+    for (int i = 0; i < NF; ++i)
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc) {
+            ax[i][cc] = fma(2.0, vt[i][cc], ax[i][cc]);
+            av[i][cc] = fma(2.0, kv[i][cc], av[i][cc]);
+            xt[i][cc] = fma(h, vt[i][cc], x[i][cc]);
+            vt[i][cc] = fma(h, kv[i][cc], v[i][cc]);
+        }
+    mode_rhs<NF, NC>(r + 3 * SW, kval, xt, vt, kv);
+#pragma unroll
+    for (int i = 0; i < NF; ++i)
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc) {
+            x[i][cc] = fma(h6, ax[i][cc] + vt[i][cc], x[i][cc]);
+            v[i][cc] = fma(h6, av[i][cc] + kv[i][cc], v[i][cc]);
+        }
+}
+
+template <int NF, int NC, bool FACT>
+__device__ __forceinline__ void rk4_step(const double* __restrict__ r, double kval, double h, double hh,
+                                         double h6, double (&x)[NF][NC], double (&v)[NF][NC]) {
+    if constexpr (FACT) rk4_step_factored<NF, NC>(r, kval, h, hh, h6, x, v);
+    else rk4_step_dense<NF, NC>(r, kval, h, hh, h6, x, v);
+}
+
 // nf >= 5: cap the registers at 168 so three 128-thread CTAs fit an SM (12 warps instead of 8;
 // measured +3 % at nf = 8; a cap of 128 registers spills and is slower)
 #ifndef PF_FO_MINB
@@ -274,7 +328,7 @@ __device__ __forceinline__ void fo_consume(const FoArgs& a, int64_t bx, int j, c
         const int64_t base = a.t0 + c * CH;
         const int64_t cnt = (a.t1 - base) < CH ? (a.t1 - base) : CH;
         const uint32_t bytes = (uint32_t)(cnt * REC * sizeof(double));
-        if (progress) wait_progress(progress, base + cnt);
+        if (progress) wait_progress(progress, base + cnt, a.flags);
         mbar_expect_tx(&bars[buf], bytes);
         bulk_g2s(&srec[buf][0], a.rec + base * REC, bytes, &bars[buf]);
     };
@@ -321,6 +375,18 @@ __device__ __forceinline__ void fo_consume(const FoArgs& a, int64_t bx, int j, c
         const int cnt = (int)((a.t1 - base) < CH ? (a.t1 - base) : CH);
         for (int q = 0; q < cnt; ++q) {
             const int64_t n = base + q;
+            if (n > ts && n != next_out) {
+                // tight run (strided / state-only launches, bound by the fp64 pipe): this mode is
+                // running and no row is stored before `lim`: nothing but record loads and RK4
+                int64_t lim = next_out - base < (int64_t)cnt ? next_out - base : (int64_t)cnt;
+                if (a.T - 1 - base < lim) lim = a.T - 1 - base;
+                if (lim > q) {
+                    const int qe = (int)lim;
+                    for (; q < qe; ++q) rk4_step<NF, NC, FACT>(&srec[buf][q * REC], kval, h, hh, h6, x, v);
+                    --q;                              // the for statement steps to qe
+                    continue;
+                }
+            }
             const double* __restrict__ r = &srec[buf][q * REC];
             const bool out = (n == next_out);
             if (n < ts) {
@@ -392,49 +458,7 @@ __device__ __forceinline__ void fo_consume(const FoArgs& a, int64_t bx, int j, c
                 }
                 if (n + 1 < a.T) {
                     // one classical RK4 step n -> n+1                      rk4.py:27-55
-                    if constexpr (FACT) {
-                        rk4_step_factored<NF, NC>(r, kval, h, hh, h6, x, v);
-                    } else {
-                        double kv[NF][NC], ax[NF][NC], av[NF][NC], xt[NF][NC], vt[NF][NC];
-                        mode_rhs<NF, NC>(r, kval, x, v, kv);
-#pragma unroll
-                        for (int i = 0; i < NF; ++i)
-#pragma unroll
-                            for (int cc = 0; cc < NC; ++cc) {
-                                ax[i][cc] = v[i][cc];
-                                av[i][cc] = kv[i][cc];
-                                xt[i][cc] = fma(hh, v[i][cc], x[i][cc]);
-                                vt[i][cc] = fma(hh, kv[i][cc], v[i][cc]);
-                            }
-                        mode_rhs<NF, NC>(r + SW, kval, xt, vt, kv);
-#pragma unroll
-                        for (int i = 0; i < NF; ++i)
-#pragma unroll
-                            for (int cc = 0; cc < NC; ++cc) {
-                                ax[i][cc] = fma(2.0, vt[i][cc], ax[i][cc]);
-                                av[i][cc] = fma(2.0, kv[i][cc], av[i][cc]);
-                                xt[i][cc] = fma(hh, vt[i][cc], x[i][cc]);
-                                vt[i][cc] = fma(hh, kv[i][cc], v[i][cc]);
-                            }
-                        mode_rhs<NF, NC>(r + 2 * SW, kval, xt, vt, kv);
-#pragma unroll
-                        for (int i = 0; i < NF; ++i)
-#pragma unroll
-                            for (int cc = 0; cc < NC; ++cc) {
-                                ax[i][cc] = fma(2.0, vt[i][cc], ax[i][cc]);
-                                av[i][cc] = fma(2.0, kv[i][cc], av[i][cc]);
-                                xt[i][cc] = fma(h, vt[i][cc], x[i][cc]);
-                                vt[i][cc] = fma(h, kv[i][cc], v[i][cc]);
-                            }
-                        mode_rhs<NF, NC>(r + 3 * SW, kval, xt, vt, kv);
-#pragma unroll
-                        for (int i = 0; i < NF; ++i)
-#pragma unroll
-                            for (int cc = 0; cc < NC; ++cc) {
-                                x[i][cc] = fma(h6, ax[i][cc] + vt[i][cc], x[i][cc]);
-                                v[i][cc] = fma(h6, av[i][cc] + kv[i][cc], v[i][cc]);
-                            }
-                    }
+                    rk4_step<NF, NC, FACT>(r, kval, h, hh, h6, x, v);
                 }
             }
             if (out) {

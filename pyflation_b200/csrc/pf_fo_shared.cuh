@@ -56,14 +56,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // Fused launches: records are produced by another CTA of the same grid; wait (acquire) until
 // `need` of them are published, then order the generic-proxy writes before the TMA read.
-__device__ __forceinline__ void wait_progress(const long long* progress, long long need) {
+// A wait that outlasts ~20 s (the producer died, or the CTAs were not co-resident under a
+// debugger / profiler) does not hang and does not kill the context: it sets PF_FLAG_TIMEOUT in
+// the flags word and lets the CTA run on, so the host raises from check_flags() and can retry
+// with PF_FO_NOFUSE (three plain launches, no inter-CTA protocol).
+constexpr unsigned PF_SPIN_LIMIT = 1u << 27;
+
+__device__ __forceinline__ void wait_progress(const long long* progress, long long need, int32_t* flags) {
     long long have;
     unsigned spins = 0;
     for (;;) {
         asm volatile("ld.acquire.gpu.global.s64 %0, [%1];" : "=l"(have) : "l"(progress) : "memory");
         if (have >= need) break;
         __nanosleep(128);
-        if (++spins > (1u << 27)) __trap();           // ~20 s: the producer died; fail, do not hang
+        if (++spins > PF_SPIN_LIMIT) {
+            if (flags) atomicOr(flags, PF_FLAG_TIMEOUT);
+            break;
+        }
     }
     asm volatile("fence.proxy.async;" ::: "memory");
 }

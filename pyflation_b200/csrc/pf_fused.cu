@@ -42,6 +42,9 @@ __device__ __forceinline__ void fo_produce(const FoArgs& a, const ProdArgsN& f) 
     const int64_t T = a.T, n0 = f.n0;
     long long* progress = reinterpret_cast<long long*>(f.ws + 2);
     if (tid == 0) s_head = n0;
+    // records of rows before n0 are NaN, exactly as pf_stage_table leaves them
+    for (int64_t i = tid; i < n0 * REC; i += FUSED_PROD_THREADS) f.rec[i] = qnan();
+    __threadfence();
     asm volatile("bar.sync 2, %0;" ::"n"(FUSED_PROD_THREADS) : "memory");
 
     if (tid < 32) {
@@ -80,7 +83,7 @@ __device__ __forceinline__ void fo_produce(const FoArgs& a, const ProdArgsN& f) 
         const int64_t need = (b + 32 < T) ? b + 32 : T;
         unsigned spins = 0;
         while (s_head < need) {
-            if (++spins > (1u << 30)) __trap();
+            if (++spins > (1u << 30)) { atomicOr(f.ws + 1, PF_FLAG_TIMEOUT); break; }
         }
         __threadfence_block();                            // stage arguments are read after s_head
         for (int item = w; item < 128; item += FUSED_WORKERS) {

@@ -222,6 +222,11 @@ class FirstOrderProblem(object):
 
     def check_flags(self):
         f = int(self.flags.item())
+        if f & _lib.PF_FLAG_TIMEOUT:
+            raise _lib.LibraryError(
+                "fused first-order launch: a CTA gave up waiting for the producer / its lock-step "
+                "partners (instrumented or time-sliced run?); the result is invalid -- rerun with "
+                "PF_FO_NOFUSE=1 (three plain launches)")
         if f & _lib.PF_FLAG_BG_MISMATCH:
             raise NotImplementedError(
                 "first-order start vector: the background rows of some column are not on column "
@@ -325,14 +330,18 @@ def first_order_host(prob, out=None, slab_bytes=1 << 30, ring=None, y0=None, n0=
     npert = nvar - nb
     compact = bool(compact and ring is None and prob.tsix_host is not None
                    and prob.ystart_host is not None)
+    # cudaMemcpy2D pitches stop at 2 GiB: very wide rows take the full-row copies
+    if compact and nvar * nk * 16 >= (1 << 31):
+        compact = False
     rows_per_t = npert if compact else nvar
     W = plan_window(T, rows_per_t, nk, slab_bytes)
     if ring is not None:
         W = max(1, min(W, ring.shape[0] // 2))
     elif out is None:
         out = _pinned_empty((T, nvar, nk), torch.complex128)
-    elif tuple(out.shape) != (T, nvar, nk) or out.dtype != torch.complex128 or not out.is_contiguous():
-        raise ValueError("output buffer must be a contiguous complex128 tensor of shape %r"
+    elif (tuple(out.shape) != (T, nvar, nk) or out.dtype != torch.complex128 or not out.is_contiguous()
+          or out.device.type != "cpu"):
+        raise ValueError("output buffer must be a contiguous complex128 CPU tensor of shape %r"
                          % ((T, nvar, nk),))
     layout = _lib.PF_LAYOUT_PERT if compact else _lib.PF_LAYOUT_FULL
     # start rows sorted in k (the normal case): in every window the started modes are a prefix
@@ -341,85 +350,94 @@ def first_order_host(prob, out=None, slab_bytes=1 << 30, ring=None, y0=None, n0=
     filler = None
     fill_rc = []
     d2h_bytes = 0
-    with torch.cuda.device(prob.dev):
-        slabs = [torch.empty((W, rows_per_t, nk), dtype=torch.complex128, device=prob.dev)
-                 for _ in range(2 if W < T else 1)]
-        compute = torch.cuda.current_stream()
-        copier = torch.cuda.Stream()
-        copied = [None, None]
-        w = 0
-        for t0 in range(0, T, W):
-            t1 = min(T, t0 + W)
-            b = w % len(slabs)
-            if copied[b] is not None:
-                compute.wait_event(copied[b])           # slab b is free again
-            if t0 == 0 and y0 is not None:
-                prob.solve(y0, n0, t1, slabs[b], 1, compute, layout)   # K1 + K1b ride along
-            else:
-                prob.launch(t0, t1, slabs[b], 1, compute, layout)
-            if pr_out is not None:
-                for r0 in range(t0, t1, 32768):
-                    r1 = min(t1, r0 + 32768)
-                    if compact:
-                        _lib.check(L.pf_pr_spectrum_pert(nf, r1 - r0, nk, _ptr(slabs[b][r0 - t0:r1 - t0]),
-                                                         _ptr(prob.rec), prob.rec.shape[1],
-                                                         int(L.pf_rec_bg_offset(nf)), r0, None,
-                                                         _ptr(pr_out[r0:r1]), _stream_ptr(compute)))
-                    else:
-                        _lib.check(L.pf_pr_spectrum(nf, r1 - r0, nk, _ptr(slabs[b][r0 - t0:r1 - t0]), None,
-                                                    _ptr(pr_out[r0:r1]), _stream_ptr(compute)))
-            done = torch.cuda.Event()
-            done.record(compute)
-            copier.wait_event(done)
-            with torch.cuda.stream(copier):
-                if compact and sorted_starts:
-                    kcols = int(np.searchsorted(prob.tsix_host, t1 - 1, side="right"))
-                    d2h_bytes += npert * kcols * 16 * (t1 - t0)
-                    for r in range(npert if kcols else 0):       # one pitched copy per variable row
-                        dst = out.data_ptr() + ((t0 * nvar + nb + r) * nk) * 16
-                        _lib.check(L.pf_copy_rows_d2h(ctypes.c_void_p(dst), nvar * nk * 16,
-                                                      ctypes.c_void_p(slabs[b].data_ptr() + r * nk * 16),
-                                                      npert * nk * 16, kcols * 16, t1 - t0,
-                                                      _stream_ptr(copier)))
-                elif compact:
-                    d2h_bytes += npert * nk * 16 * (t1 - t0)
-                    dst = out.data_ptr() + (t0 * nvar + nb) * nk * 16
-                    _lib.check(L.pf_copy_rows_d2h(ctypes.c_void_p(dst), nvar * nk * 16, _ptr(slabs[b]),
-                                                  npert * nk * 16, npert * nk * 16, t1 - t0,
-                                                  _stream_ptr(copier)))
+    try:
+        with torch.cuda.device(prob.dev):
+            slabs = [torch.empty((W, rows_per_t, nk), dtype=torch.complex128, device=prob.dev)
+                     for _ in range(2 if W < T else 1)]
+            compute = torch.cuda.current_stream()
+            copier = torch.cuda.Stream()
+            copied = [None, None]
+            w = 0
+            for t0 in range(0, T, W):
+                t1 = min(T, t0 + W)
+                b = w % len(slabs)
+                if copied[b] is not None:
+                    compute.wait_event(copied[b])           # slab b is free again
+                if t0 == 0 and y0 is not None:
+                    prob.solve(y0, n0, t1, slabs[b], 1, compute, layout)   # K1 + K1b ride along
                 else:
-                    d2h_bytes += nvar * nk * 16 * (t1 - t0)
-                    dst = out[t0:t1] if ring is None else ring[(w % 2) * W:(w % 2) * W + (t1 - t0)]
-                    dst.copy_(slabs[b][:t1 - t0], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copier)
-            copied[b] = ev
-            if compact and t0 == 0:
-                # the step records (background rows included) are complete once window 0 is:
-                # bring them over and let the host threads write the background rows of every
-                # time step while the remaining windows compute and copy
-                rec_host = prob.rec.cpu().numpy()
-                d2h_bytes += rec_host.nbytes
-                bg_off = int(L.pf_rec_bg_offset(nf))
-                # share the host cores between the ranks of one box (torchrun sets LOCAL_WORLD_SIZE)
-                local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-                nthreads = fill_threads or max(1, len(os.sched_getaffinity(0)) // local_world)
+                    prob.launch(t0, t1, slabs[b], 1, compute, layout)
+                if pr_out is not None:
+                    for r0 in range(t0, t1, 32768):
+                        r1 = min(t1, r0 + 32768)
+                        if compact:
+                            _lib.check(L.pf_pr_spectrum_pert(nf, r1 - r0, nk, _ptr(slabs[b][r0 - t0:r1 - t0]),
+                                                             _ptr(prob.rec), prob.rec.shape[1],
+                                                             int(L.pf_rec_bg_offset(nf)), r0, None,
+                                                             _ptr(pr_out[r0:r1]), _stream_ptr(compute)))
+                        else:
+                            _lib.check(L.pf_pr_spectrum(nf, r1 - r0, nk, _ptr(slabs[b][r0 - t0:r1 - t0]), None,
+                                                        _ptr(pr_out[r0:r1]), _stream_ptr(compute)))
+                done = torch.cuda.Event()
+                done.record(compute)
+                copier.wait_event(done)
+                with torch.cuda.stream(copier):
+                    if compact and sorted_starts:
+                        kcols = int(np.searchsorted(prob.tsix_host, t1 - 1, side="right"))
+                        d2h_bytes += npert * kcols * 16 * (t1 - t0)
+                        for r in range(npert if kcols else 0):       # one pitched copy per variable row
+                            dst = out.data_ptr() + ((t0 * nvar + nb + r) * nk) * 16
+                            _lib.check(L.pf_copy_rows_d2h(ctypes.c_void_p(dst), nvar * nk * 16,
+                                                          ctypes.c_void_p(slabs[b].data_ptr() + r * nk * 16),
+                                                          npert * nk * 16, kcols * 16, t1 - t0,
+                                                          _stream_ptr(copier)))
+                    elif compact:
+                        d2h_bytes += npert * nk * 16 * (t1 - t0)
+                        dst = out.data_ptr() + (t0 * nvar + nb) * nk * 16
+                        _lib.check(L.pf_copy_rows_d2h(ctypes.c_void_p(dst), nvar * nk * 16, _ptr(slabs[b]),
+                                                      npert * nk * 16, npert * nk * 16, t1 - t0,
+                                                      _stream_ptr(copier)))
+                    else:
+                        d2h_bytes += nvar * nk * 16 * (t1 - t0)
+                        dst = out[t0:t1] if ring is None else ring[(w % 2) * W:(w % 2) * W + (t1 - t0)]
+                        dst.copy_(slabs[b][:t1 - t0], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copier)
+                copied[b] = ev
+                if compact and t0 == 0:
+                    # the step records (background rows included) are complete once window 0 is:
+                    # bring them over and let the host threads write the background rows of every
+                    # time step while the remaining windows compute and copy
+                    rec_host = prob.rec.cpu().numpy()
+                    d2h_bytes += rec_host.nbytes
+                    bg_off = int(L.pf_rec_bg_offset(nf))
+                    # share the host cores between the ranks of one box (torchrun sets LOCAL_WORLD_SIZE)
+                    local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+                    nthreads = fill_threads or max(1, len(os.sched_getaffinity(0)) // local_world)
 
-                def _fill():
-                    fill_rc.append(L.pf_host_fill_background(
-                        ctypes.c_void_p(out.data_ptr()), nf, nk, 0, T,
-                        ctypes.c_void_p(rec_host.ctypes.data), rec_host.shape[1], bg_off,
-                        ctypes.c_void_p(prob.tsix_host.ctypes.data),
-                        ctypes.c_void_p(prob.ystart_host.ctypes.data), 1 if sorted_starts else 0,
-                        nthreads))
-                filler = threading.Thread(target=_fill)
-                filler.start()
-            w += 1
-        copier.synchronize()
-        compute.synchronize()
+                    def _fill():
+                        rc = L.pf_host_fill_background(
+                            ctypes.c_void_p(out.data_ptr()), nf, nk, 0, T,
+                            ctypes.c_void_p(rec_host.ctypes.data), rec_host.shape[1], bg_off,
+                            ctypes.c_void_p(prob.tsix_host.ctypes.data),
+                            ctypes.c_void_p(prob.ystart_host.ctypes.data), 1 if sorted_starts else 0,
+                            nthreads)
+                        # the error text is thread-local in the library: read it on this thread
+                        fill_rc.append((rc, L.pf_last_error().decode("utf-8", "replace") if rc else ""))
+                    filler = threading.Thread(target=_fill)
+                    filler.start()
+                w += 1
+            copier.synchronize()
+            compute.synchronize()
+    finally:
+        # never leave the host threads streaming into `out` behind an exception
+        if filler is not None:
+            filler.join()
     if filler is not None:
         filler.join()
-        _lib.check(fill_rc[0])
+        rc, msg = fill_rc[0]
+        if rc:
+            raise (_lib.ArgumentError(rc, msg) if rc < 0 else _lib.LibraryError(msg))
     prob.d2h_bytes = d2h_bytes                  # what actually crossed PCIe towards the host
     prob.h2d_bytes = prob.k.numel() * 8 + prob.tsix.numel() * 8 + prob.ystart.numel() * 16
     return out if ring is None else ring
