@@ -548,8 +548,8 @@ def run_gpu_arm(args):
         cpu_baseline = {"value": work / wall, "unit": UNIT, "cores": arm.cores, "kind": "port",
                         "sample": arm.sample, "wall_s": wall}
 
-    if os.environ.get("NCCL_DEBUG", "VERSION") == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line
+    if os.environ.get("NCCL_DEBUG") in ("VERSION", "WARN"):
+        del os.environ["NCCL_DEBUG"]             # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)

@@ -95,18 +95,36 @@ def test_argument_errors_without_gpu():
         engine.make_model("hybridquadratic", {}, 1)
 
 
-@pytest.mark.parametrize("nf,pert_nan", [(1, 0), (1, 1), (2, 1), (3, 0)])
-def test_host_fill_background_on_cpu(nf, pert_nan):
+def test_host_fill_narrower_store_widths():
+    """The store width of the run-based fill is chosen once per process (AVX-512 / AVX2 / SSE2):
+    rerun the sorted cases in child processes that force the narrower ones."""
+    import subprocess, sys
+    for isa in ("sse2", "avx2"):
+        res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", __file__, "-k",
+                              "test_host_fill_background_on_cpu and True"],
+                             env=dict(os.environ, PF_HOST_FILL_ISA=isa), capture_output=True, text=True,
+                             timeout=600)
+        assert res.returncode == 0, isa + res.stdout[-2000:] + res.stderr[-2000:]
+        assert "5 passed" in res.stdout
+
+
+@pytest.mark.parametrize("sorted_starts", [False, True])
+@pytest.mark.parametrize("nf,pert_nan", [(1, 0), (1, 1), (2, 1), (3, 0), (10, 1)])
+def test_host_fill_background_on_cpu(nf, pert_nan, sorted_starts):
     """pf_host_fill_background is host code: checked here without a GPU against a NumPy
-    construction (unsorted start rows, odd sizes, several thread counts)."""
+    construction (unsorted start rows -> per-element path; sorted -> run-based path with the
+    widest non-temporal stores of this CPU; odd sizes, several thread counts, nf = 10 -> the
+    any-nfields fallback)."""
     from pyflation_b200 import _lib
     L = _lib.lib()
     rng = np.random.RandomState(3 + nf)
     T, nk = 37, 53
     nb, nvar = 2 * nf + 1, 2 * nf * nf + 2 * nf + 1
-    rec_len, bg_off = int(L.pf_rec_doubles(nf)), 4 * (2 + nf * nf)
+    rec_len, bg_off = int(L.pf_rec_doubles(nf)), int(L.pf_rec_bg_offset(nf))
     rec = rng.standard_normal((T, rec_len))
     tsix = rng.randint(0, T + 5, nk).astype(np.int64)          # some modes never start
+    if sorted_starts:
+        tsix = np.sort(tsix)
     ystart = rng.standard_normal((nvar, nk)) + 1j * rng.standard_normal((nvar, nk))
     want = np.full((T, nvar, nk), 7.0 + 7.0j)
     for t in range(T):
