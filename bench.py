@@ -733,6 +733,38 @@ def run_e2e(args, m, T, nvar, mode_steps, world, rank, barrier):
     if full:
         last = host[T - 1].numpy()
         assert np.isfinite(last[3:]).all()
+    # where the time goes (N = 1): the PCIe copies alone, the host fill alone
+    breakdown = None
+    if full and world == 1:
+        import ctypes
+        from pyflation_b200 import _lib
+        pm = engine.make_model(POTENTIAL, POT_PARAMS, NFIELDS, m.ainit)
+        y0b, n0b = np.real(ystart_host[0:3, 0]).copy(), int(tsix_host.min())
+        os.environ["PF_PROBE_NO_FILL"] = "1"
+        try:
+            t0 = time.perf_counter()
+            prob = engine.FirstOrderProblem(pm, m.k, tsix_host, ystart_host, 0.0, T, H)
+            engine.first_order_host(prob, out=host, y0=y0b, n0=n0b)
+            torch.cuda.synchronize()
+            dma_ms = 1e3 * (time.perf_counter() - t0)
+        finally:
+            del os.environ["PF_PROBE_NO_FILL"]
+        rec_host = prob.rec.cpu().numpy()
+        L = _lib.lib()
+        t0 = time.perf_counter()
+        rc = L.pf_host_fill_background(ctypes.c_void_p(host.data_ptr()), NFIELDS, NK_PER_GPU, 0, T,
+                                       ctypes.c_void_p(rec_host.ctypes.data), rec_host.shape[1],
+                                       int(L.pf_rec_bg_offset(NFIELDS)), ctypes.c_void_p(tsix_host.ctypes.data),
+                                       ctypes.c_void_p(ystart_host.ctypes.data), 1,
+                                       len(os.sched_getaffinity(0)))
+        fill_ms = 1e3 * (time.perf_counter() - t0)
+        assert rc == 0
+        d2h_b = float(prob.d2h_bytes)
+        breakdown = {"pcie_copies_alone_ms": dma_ms, "pcie_GBs": d2h_b / dma_ms / 1e6,
+                     "host_fill_alone_ms": fill_ms, "host_fill_GBs": (need - d2h_b) / fill_ms / 1e6,
+                     "host_threads": len(os.sched_getaffinity(0)),
+                     "note": "both together share the host memory system: the step time above is "
+                             "neither's sum nor their max; N ranks of one box share the same host DRAM"}
     h2d = int(ystart_host.size * 16 + m.k.size * 8 + tsix_host.size * 8)
     moved = dict(rk4.last_transfer)
     # full layout: every row crosses PCIe; compact (default when the host can hold the result):
@@ -743,7 +775,7 @@ def run_e2e(args, m, T, nvar, mode_steps, world, rank, barrier):
     return {"value": float(ww[0]) * nsteps / float(tt[0]), "unit": UNIT,
             "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
             "host_result_bytes_per_step": int(need) * world, "steps": nsteps,
-            "ms_per_step": 1e3 * float(tt[0]) / nsteps,
+            "ms_per_step": 1e3 * float(tt[0]) / nsteps, "breakdown": breakdown,
             "host_buffer": "full pinned yresult" if full else "pinned ring (host RAM too small for N full results)",
             "api": "rk4.rkdriver_tsix(ystart, simtstart, tsix, tend, h, derivs=CanonicalFirstOrder.derivs, "
                    "yresult_out=<pinned buffer>)" if full else "engine.first_order_host(ring=...)"}

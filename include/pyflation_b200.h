@@ -157,7 +157,9 @@ int pf_stage_table(const pf_model *m, int64_t T, double simtstart, double h, int
  *   kernel then writes its columns straight into the assembled [rows][nvar][out_pitch] array,
  *   which may live on another GPU of the box (peer memory, see pf_peer_*), i.e. the k-gather
  *   rides on the kernel's own stores over NVLink instead of a separate collective.
- *   flags_dev: int32, OR-ed with PF_FLAG_* (may be NULL). */
+ *   flags_dev: int32[4] (may be NULL): [0] is OR-ed with PF_FLAG_*; [3] is scratch for the
+ *   lock-step barrier of full-trajectory launches (zeroed by the call; with NULL the launch
+ *   runs without lock-step).  pf_fo_solve's ws_dev + 1 has this layout. */
 int pf_fo_run(const pf_model *m, int64_t nk, const double *k_dev, const int64_t *tsix_dev,
               const double *ystart_dev, const double *rec_dev, int64_t T, double h,
               int64_t t0, int64_t t1, double *state_dev, double *yout_dev, int64_t out_every,

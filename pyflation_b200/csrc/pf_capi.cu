@@ -72,6 +72,17 @@ int check_model(const pf_model* m) {
     return PF_OK;
 }
 
+int sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
 int rec_kind(const pf_model* m) {
     static const bool dense_only = getenv("PF_FO_DENSE") != nullptr;
     if (m->nfields > PF_MAX_NFIELDS) return PF_REC_FACTORED;       // runtime-nf kernels: factored only

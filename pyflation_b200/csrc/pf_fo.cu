@@ -72,6 +72,7 @@ extern "C" int pf_fo_run(const pf_model* m, int64_t nk, const double* k_dev, con
     a.T = T; a.t0 = t0; a.t1 = t1; a.state = state_dev;
     a.yout = out_every > 0 ? yout_dev : nullptr; a.out_every = out_every; a.flags = flags_dev;
     a.h = h;
+    a.lockstep = flags_dev ? flags_dev + 3 : nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     static const bool generic_only = getenv("PF_FO_GENERIC") != nullptr;
     const bool fact = rec_kind(m) == PF_REC_FACTORED;   // must match the records pf_stage_table wrote
@@ -128,7 +129,7 @@ extern "C" int pf_fo_solve(const pf_model* m, int64_t nk, const double* k_dev, c
         a.nk = nk; a.k = k_dev; a.tsix = tsix_dev; a.ystart = ystart_dev; a.rec = rec;
         a.T = T; a.t0 = 0; a.t1 = t1; a.state = state_dev;
         a.yout = out_every > 0 ? yout_dev : nullptr; a.out_every = out_every;
-        a.flags = ws_dev + 1; a.h = h; a.layout = layout; a.opitch = out_pitch ? out_pitch : nk;
+        a.flags = ws_dev + 1; a.h = h; a.layout = layout; a.opitch = out_pitch ? out_pitch : nk; a.lockstep = nullptr;
         if (launch_fo1_fused(m, a, simtstart, n0, y0_host, rec, ws_dev, st)) {
             PF_CUDA_CHECK(cudaGetLastError(), "pf_fo_solve fused launch");
             return PF_OK;
@@ -139,7 +140,7 @@ extern "C" int pf_fo_solve(const pf_model* m, int64_t nk, const double* k_dev, c
         a.nk = nk; a.k = k_dev; a.tsix = tsix_dev; a.ystart = ystart_dev; a.rec = rec;
         a.T = T; a.t0 = 0; a.t1 = t1; a.state = state_dev;
         a.yout = out_every > 0 ? yout_dev : nullptr; a.out_every = out_every;
-        a.flags = ws_dev + 1; a.h = h; a.layout = layout; a.opitch = out_pitch ? out_pitch : nk;
+        a.flags = ws_dev + 1; a.h = h; a.layout = layout; a.opitch = out_pitch ? out_pitch : nk; a.lockstep = nullptr;
         if (launch_fo_fused_generic(m, a, simtstart, n0, y0_host, rec, stagey, ws_dev, st)) {
             PF_CUDA_CHECK(cudaGetLastError(), "pf_fo_solve fused launch");
             return PF_OK;

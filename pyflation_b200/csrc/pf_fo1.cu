@@ -83,33 +83,6 @@ __device__ __forceinline__ void rk4_mode(const Coef& c, double kval, double h, d
 // and waits until all consumers of this epoch have arrived.
 constexpr int FO1_LOCKSTEP_ROWS = 512;
 
-struct LockStep {
-    int* counter;                                     // null: no lock-step
-    int nconsumers;
-    int rows;                                         // barrier period
-    int32_t* flags;                                   // PF_FLAG_TIMEOUT goes here
-};
-
-__device__ __forceinline__ void lockstep_barrier(const LockStep& ls, int64_t row) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int target = (int)((row / ls.rows) + 1) * ls.nconsumers;
-        asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ls.counter) : "memory");
-        int have;
-        unsigned spins = 0;
-        for (;;) {
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(have) : "l"(ls.counter) : "memory");
-            if (have >= target) break;
-            __nanosleep(64);
-            if (++spins > PF_SPIN_LIMIT) {
-                if (ls.flags) atomicOr(ls.flags, PF_FLAG_TIMEOUT);
-                break;
-            }
-        }
-    }
-    __syncthreads();
-}
-
 struct Fo1Smem {                                      // one per CTA, owned by the kernel
     alignas(128) double srec[2][FO1_CH * FO1_REC];
     alignas(8) uint64_t bars[2];
@@ -119,7 +92,7 @@ struct Fo1Smem {                                      // one per CTA, owned by t
 template <bool PERT>
 __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nthreads,
                                             const long long* progress, Fo1Smem& sm,
-                                            const LockStep ls = LockStep{nullptr, 0, FO1_LOCKSTEP_ROWS, nullptr}) {
+                                            const LockStep ls = LockStep{nullptr, 0, FO1_LOCKSTEP_ROWS, nullptr, 0}) {
     constexpr int NV = PERT ? 2 : 5;                  // rows per time step in the output
     constexpr int XO = PERT ? 0 : 3;                  // row of dphi within a time step
     double (&srec)[2][FO1_CH * FO1_REC] = sm.srec;
@@ -178,7 +151,7 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
             prow += rstride;
             if ((r - a.t0) % ls.rows == ls.rows - 1) lockstep_barrier(ls, r - a.t0);
         }
-        next_out = nan_end;
+        next_out = nan_end > a.t0 ? nan_end : a.t0;
     } else {
         for (; next_out < nan_end; next_out += every) {
             if (live) {
@@ -188,7 +161,9 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
             prow += rstride;
         }
     }
-    int64_t n = nan_end;
+    // a window that begins after this CTA's first start row resumes at t0 from the carried state
+    // (it used to re-integrate from the start row: same bits, wasted steps)
+    int64_t n = nan_end > a.t0 ? nan_end : a.t0;
     if (n >= a.t1) return;
 
     // ---- regimes 2 and 3: records streamed through shared memory from row c0 on
@@ -309,6 +284,18 @@ template <bool PERT>
 __global__ void __launch_bounds__(512) fo1_kernel(FoArgs a) {
     __shared__ Fo1Smem sm;
     fo1_consume<PERT>(a, blockIdx.x, blockDim.x, nullptr, sm);
+}
+
+// Lock-step launch of the plain kernel (full-trajectory windows, and solves whose records already
+// exist): cooperative, one 512-thread CTA per k tile, the whole grid co-resident (at most one CTA
+// per SM), all CTAs advancing through the rows together.  Batches wider than one such wave do
+// NOT use it: persistent CTAs taking several tiles in turn were measured slower than the plain
+// multi-wave launch (2^20 modes, 1024-row window: 14.0 vs 12.7 ms; profiles/r2_ab_lockstep.txt).
+template <bool PERT>
+__global__ void __launch_bounds__(512) fo1_lockstep_kernel(FoArgs a) {
+    __shared__ Fo1Smem sm;
+    const LockStep ls{a.lockstep, (int)gridDim.x, FO1_LOCKSTEP_ROWS, a.flags, 0};
+    fo1_consume<PERT>(a, blockIdx.x, blockDim.x, nullptr, sm, ls);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -441,24 +428,13 @@ __global__ void __launch_bounds__(512) fo1_fused_kernel(FoArgs a, ProdArgs f, in
     }
     const long long* progress = reinterpret_cast<const long long*>(f.ws + 2);
     __shared__ Fo1Smem sm;
-    const LockStep ls{lockstep ? f.ws + 4 : nullptr, (int)gridDim.x - 1, lockstep > 1 ? lockstep : FO1_LOCKSTEP_ROWS, f.ws + 1};
+    const LockStep ls{lockstep ? f.ws + 4 : nullptr, (int)gridDim.x - 1, lockstep > 1 ? lockstep : FO1_LOCKSTEP_ROWS, f.ws + 1, 0};
     if (a.layout == PF_LAYOUT_PERT) fo1_consume<true>(a, cta - 1, cthreads, progress, sm, ls);
     else fo1_consume<false>(a, cta - 1, cthreads, progress, sm, ls);
 }
 
 // Grid shape: a whole number c of CTAs per SM, c the smallest for which a CTA holds at most
 // `max_threads` threads (so every SM gets the same number of equally sized CTAs).
-static int sm_count() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
-}
-
 // CTA size.  Full-trajectory launches are bound by the DRAM write pattern: 512-thread CTAs make
 // every row segment of a CTA an aligned 8 KB block (measured with lock-step on three different
 // B200s: 5.78-5.93 ms vs 6.21-6.26 ms for the balanced 448-thread grid), so they are used
@@ -484,6 +460,18 @@ static int64_t fo1_block(int64_t nk, int sms, int64_t out_every) {
 }
 
 int launch_fo1(const FoArgs& a, cudaStream_t st) {
+    static const bool no_lockstep = getenv("PF_FO1_NOLOCKSTEP") != nullptr;
+    const int64_t ntiles = (a.nk + 511) / 512;
+    if (a.lockstep && !no_lockstep && a.out_every == 1 && a.nk >= 16384 && ntiles <= sm_count() &&
+        a.t1 - a.t0 >= 2 * FO1_LOCKSTEP_ROWS) {
+        FoArgs aa = a;
+        void* args[] = {&aa};
+        void* fn = a.layout == PF_LAYOUT_PERT ? (void*)fo1_lockstep_kernel<true> : (void*)fo1_lockstep_kernel<false>;
+        if (cudaMemsetAsync(a.lockstep, 0, sizeof(int32_t), st) == cudaSuccess &&
+            cudaLaunchCooperativeKernel(fn, dim3((unsigned)ntiles), dim3(512), args, 0, st) == cudaSuccess)
+            return 0;
+        (void)cudaGetLastError();
+    }
     const int64_t block = fo1_block(a.nk, sm_count(), a.out_every);
     const int64_t grid = (a.nk + block - 1) / block;
     if (a.layout == PF_LAYOUT_PERT) fo1_kernel<true><<<(unsigned)grid, (unsigned)block, 0, st>>>(a);

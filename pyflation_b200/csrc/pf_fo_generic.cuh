@@ -299,6 +299,12 @@ __device__ __forceinline__ void rk4_step(const double* __restrict__ r, double kv
 #endif
 // Consumer: integrates column j of the mode matrix for the k tile bx.  `progress` (may be null)
 // is the producer's published record count in fused launches (pf_fused.cu).
+// (A persistent, time-lock-stepped variant of this consumer -- one co-resident wave of CTAs looping
+// over (k tile, column) work items, as pf_fo1.cu does for nf = 1 -- was measured on B200 and is
+// NOT used: nf = 2 full trajectory 20.4 vs 15.6 ms, nf = 8 40.1 vs 31.6 ms.  With several CTAs per
+// SM the hardware's own back-filling of finished CTAs beats fixed passes whose last one is
+// partly empty, and the 13 / 145 rows per time step already spread the stores evenly;
+// profiles/r2_ab_lockstep.txt.)
 template <int NF, int NC, bool FACT = false>
 __device__ __forceinline__ void fo_consume(const FoArgs& a, int64_t bx, int j, const long long* progress) {
     using S = FoShape<NF>;

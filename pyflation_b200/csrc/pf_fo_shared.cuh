@@ -19,6 +19,7 @@ struct FoArgs {
     int32_t* flags;
     double h;
     int32_t layout;                      // PF_LAYOUT_FULL or PF_LAYOUT_PERT
+    int32_t* lockstep;                   // arrival counter of a persistent lock-step launch, or null
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -77,8 +78,40 @@ __device__ __forceinline__ void wait_progress(const long long* progress, long lo
     asm volatile("fence.proxy.async;" ::: "memory");
 }
 
+// Time lock-step of co-resident consumer CTAs (full-trajectory launches): a monotonically
+// increasing arrival counter in global memory; thread 0 adds 1 and waits until all consumers of
+// this epoch have arrived (`base`: arrivals to discount, 0 for a single pass).
+struct LockStep {
+    int* counter;                                     // null: no lock-step
+    int nconsumers;
+    int rows;                                         // barrier period
+    int32_t* flags;                                   // PF_FLAG_TIMEOUT goes here
+    int base;
+};
+
+__device__ __forceinline__ void lockstep_barrier(const LockStep& ls, int64_t row) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int target = ls.base + (int)((row / ls.rows) + 1) * ls.nconsumers;
+        asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ls.counter) : "memory");
+        int have;
+        unsigned spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(have) : "l"(ls.counter) : "memory");
+            if (have >= target) break;
+            __nanosleep(64);
+            if (++spins > PF_SPIN_LIMIT) {
+                if (ls.flags) atomicOr(ls.flags, PF_FLAG_TIMEOUT);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
+
 struct PotParams { double v[PF_MAX_PARAMS]; };
 
+int sm_count();                                      // pf_capi.cu
 int launch_fo1(const FoArgs& a, cudaStream_t st);   // pf_fo1.cu
 bool launch_fo_fused_generic(const pf_model* m, const FoArgs& a, double simtstart, int64_t n0,
                              const double* y0_host, double* rec, double* stagey, int32_t* ws,

@@ -404,7 +404,7 @@ def first_order_host(prob, out=None, slab_bytes=1 << 30, ring=None, y0=None, n0=
                     ev = torch.cuda.Event()
                     ev.record(copier)
                 copied[b] = ev
-                if compact and t0 == 0:
+                if compact and t0 == 0 and not os.environ.get("PF_PROBE_NO_FILL"):   # (probe switch: DMA alone)
                     # the step records (background rows included) are complete once window 0 is:
                     # bring them over and let the host threads write the background rows of every
                     # time step while the remaining windows compute and copy

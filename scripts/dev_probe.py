@@ -22,6 +22,21 @@ def main(pot="lambdaphi4", nf=1, nk=2**16, bgy=(25.0, 0.0, 0.0), params=None):
         e0.record(); prob.build_tables(y0, n0); e1.record()
         torch.cuda.synchronize()
         print("K1+K1b %.3f ms" % e0.elapsed_time(e1))
+    if os.environ.get("PF_WINDOW"):
+        # one full-output time window [t0, t1) of a windowed run (state carried in from row t0)
+        t0w, t1w = (int(v) for v in os.environ["PF_WINDOW"].split(","))
+        prob.build_tables(y0, n0)
+        prob.launch(0, t0w, None, 0)
+        state0 = prob.state.clone()
+        outw = torch.empty((t1w - t0w, prob.nvar, nk), dtype=torch.complex128, device="cuda")
+        for rep in range(4):
+            prob.state.copy_(state0)
+            e0, e1 = ev(), ev()
+            e0.record(); prob.launch(t0w, t1w, outw, 1); e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            print("WINDOW [%d,%d) %.3f ms  write %.1f GB/s" % (t0w, t1w, ms, outw.numel() * 16 / ms / 1e6))
+        prob.check_flags()
+        return
     every = int(os.environ.get("PF_EVERY", "1"))
     nrows = (T + every - 1) // every
     out = torch.empty((nrows, prob.nvar, nk), dtype=torch.complex128, device="cuda")
@@ -61,7 +76,7 @@ def main(pot="lambdaphi4", nf=1, nk=2**16, bgy=(25.0, 0.0, 0.0), params=None):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "c2"
-    if which == "c2": main()
+    if which == "c2": main(nk=int(sys.argv[2]) if len(sys.argv) > 2 else 2 ** 16)
     elif which == "c1": main("msqphisq", 1, 2053, (18.0, -0.1, 0.0))
     elif which == "c3": main("hybridquadratic", 2, int(sys.argv[2]) if len(sys.argv) > 2 else 2**16, (12.0, 1/300.0, 12.0, 49/300.0, 0))
     elif which == "c5": main("msqphisq", 1, int(sys.argv[2]) if len(sys.argv) > 2 else 2**20, (18.0, -0.1, 0.0))

@@ -28,6 +28,13 @@ def run(label, **kw):
 
 run("compact (host buffer: torch pin_memory)")
 run("compact (host buffer: torch pin_memory)")
+for nt in (2, 4, 6, 8, 12):
+    run("compact, %d fill threads" % nt, fill_threads=nt)
+os.environ["PF_PROBE_NO_FILL"] = "1"
+run("compact, DMA only (no host fill: probe)")
+del os.environ["PF_PROBE_NO_FILL"]
+if os.environ.get("PF_PROBE_SHORT"):
+    sys.exit(0)
 del host
 host = engine._pinned_empty((T, 5, nk), torch.complex128)
 print("huge-page registered buffer: pinned =", host.is_pinned())

@@ -217,6 +217,35 @@ def test_windowed_host_path_is_bitwise_identical():
     assert np.array_equal(every.view(np.float64), full[::7].view(np.float64), equal_nan=True)
 
 
+def test_unsorted_start_rows_through_the_compact_host_path():
+    """Start rows that are not sorted in k (column 0 still the earliest): the host delivery takes
+    its ``sorted_starts=False`` branch (whole perturbation rows over PCIe, per-element host fill)
+    and must give the same bits as the single-launch device trajectory, for nf = 1 and nf = 2,
+    in one window and in many."""
+    from pyflation_b200 import engine
+    for name, nk in (("c1_msqphisq_k4", 301), ("c3_hybridquadratic_2p20", 173)):
+        g = load_fo(name)
+        m, prob0 = _problem(g, k=np.linspace(KMIN, KMAX, nk))
+        rng = np.random.RandomState(5)
+        perm = np.concatenate([[0], 1 + rng.permutation(nk - 1)])
+        nf = g["nfields"]
+        pm = engine.make_model(m.potential_func, m.pot_params, nf, m.ainit)
+        tsix, ystart = m.fotstartindex[perm], np.ascontiguousarray(m.foystart[:, perm])
+        assert not np.all(np.diff(tsix) >= 0)
+        y0, n0 = np.real(ystart[:2 * nf + 1, 0]), int(tsix.min())
+        prob = engine.FirstOrderProblem(pm, m.k[perm], tsix, ystart, 0.0, prob0.T, 0.01)
+        dev = engine.first_order_device(prob, y0=y0, n0=n0).cpu().numpy()
+        for slab in (1 << 30, 3 << 20):
+            prob = engine.FirstOrderProblem(pm, m.k[perm], tsix, ystart, 0.0, prob0.T, 0.01)
+            host = engine.first_order_host(prob, slab_bytes=slab, y0=y0, n0=n0).numpy()
+            prob.check_flags()
+            assert np.array_equal(host.view(np.float64), dev.view(np.float64), equal_nan=True)
+        # and the same columns, un-permuted, as a sorted run
+        base = engine.first_order_device(prob0).cpu().numpy()
+        assert rel_err(dev[:, :2 * nf + 1], base[:, :2 * nf + 1][:, :, perm]) < 1e-13
+        assert mode_rel_err(dev, base[:, :, perm], nf) < 1e-12
+
+
 def test_fused_solve_equals_separate_kernels():
     """pf_fo_solve (producer CTA + consumers in one launch, nf = 1) against the three-kernel
     sequence pf_bg_run / pf_stage_table / pf_fo_run, and its windowed continuation."""
