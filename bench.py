@@ -629,15 +629,21 @@ def run_gpu_arm(args):
         else "fallback 6650 GB/s (B200_PROFILING.md)"
     alg_bytes = mode_steps * 16 * nvar                        # 16*nvar B per mode-step
     all_rows_bytes = float(T) * nvar * NK_PER_GPU * 16        # incl. mandatory NaN / start rows
-    traffic = None
-    try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "k2_ncu_summary.json")))
-        traffic = prof.get("dram_bytes_per_launch")
-    except Exception:
-        pass
+    # DRAM bytes per launch need profiler counters: they come from the committed ncu capture of
+    # this very launch (scripts/ncu_round2.sh -> profiles/), not from this run
+    traffic, traffic_src = None, None
+    for name in ("r2_fused_headline_ncu_full.json", "k2_ncu_summary.json"):
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", name)))
+            traffic = prof.get("dram_bytes_per_launch")
+            traffic_src = "profiles/" + name + " (ncu --set full capture of the same launch; static)"
+            break
+        except Exception:
+            pass
     roofline = {"bound": "hbm", "kernel": "fo1_fused_kernel<lambdaphi4> (K1+K1b+K2 in one launch)",
                 "achieved": alg_bytes / (k2_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": alg_bytes / (k2_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src, "kernel_ms": k2_ms,
                 "algorithmic_bytes": alg_bytes,
                 "achieved_all_rows": all_rows_bytes / (k2_ms * 1e-3) / 1e9,
