@@ -131,13 +131,13 @@ int pf_bg_run(const pf_model *m, int64_t T, double h, int64_t n0, const double *
 
 /* ---- K1b: per-step records consumed by pf_fo_run ----
  * rec_dev[T][pf_rec_doubles(nf)]:  for each RK4 stage s=0..3 of the step n -> n+1:
- * A = U/H^2,  R = 1/(a H),  C[i][l] = (V_il + phi'_i V_l + V_i phi'_l + phi'_i phi'_l U)/H^2
+ * A = U/H^2,  R2 = 1/(a H)^2,  C[i][l] = (V_il + phi'_i V_l + V_i phi'_l + phi'_i phi'_l U)/H^2
  * (cosmomodels.py:663-674), a = ainit exp(t_stage), t_stage = simtstart + n h (+ h/2, + h/2,
  * + h) (rk4.py:27-55,116-118); then the bg row n (2nf+1 doubles, at column
  * pf_rec_bg_offset(nf)); padded to an even length.  Rows n < n0 are NaN.
  * nflation with nf >= 5 stores the factors of C instead of the dense matrix -- its Hessian is
  * m^2 I (cmpotentials.py:840), so C = d I + (p g^T + g p^T + U p p^T)/H^2 with p = phi',
- * g = dU: a stage slot is (A, R, d = m^2/H^2, U, 1/H^2, 0, p[nf], g[nf]), and the mode kernel
+ * g = dU: a stage slot is (A, R2, d = m^2/H^2, U, 1/H^2, 0, p[nf], g[nf]), and the mode kernel
  * needs 4 nf + 3 multiply-adds per column for the coupling instead of nf^2.  The records are an
  * opaque contract between pf_stage_table and pf_fo_run of the same library build. */
 int pf_stage_table(const pf_model *m, int64_t T, double simtstart, double h, int64_t n0,

@@ -21,7 +21,7 @@ constexpr int FO1_CH = 64;    // steps per record chunk (64 * 128 B = 8 KB per b
 constexpr int FO1_REC = 16;
 
 struct Coef {                 // one step record, nf = 1
-    double A[4], R[4], C[4], bg[3];
+    double A[4], R[4], C[4], bg[3];                   // R = 1/(aH)^2
 };
 
 __device__ __forceinline__ Coef load_record(const double* __restrict__ r) {
@@ -36,14 +36,14 @@ __device__ __forceinline__ Coef load_record(const double* __restrict__ r) {
     return c;
 }
 
-// One classical RK4 step of  x' = v, v' = -S,  S = A v + ((kR)^2 + C) x   for one complex mode.
-__device__ __forceinline__ void rk4_mode(const Coef& c, double kval, double h, double hh, double h6,
+// One classical RK4 step of  x' = v, v' = -S,  S = A v + (k^2 R2 + C) x   for one complex mode
+// (k2 = k^2; the records hold R2 = 1/(aH)^2).
+__device__ __forceinline__ void rk4_mode(const Coef& c, double k2, double h, double hh, double h6,
                                          double (&x)[2], double (&v)[2]) {
     double B[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-        const double kr = kval * c.R[s];
-        B[s] = fma(kr, kr, c.C[s]);
+        B[s] = fma(k2, c.R[s], c.C[s]);               // k^2 / (aH)^2 + C
     }
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -116,6 +116,7 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
 
     const bool live = kk < nk;
     const double kval = live ? a.k[kk] : 0.0;
+    const double k2 = kval * kval;
     const int64_t ts = live ? a.tsix[kk] : INT64_MAX;
     double x[2] = {0.0, 0.0}, v[2] = {0.0, 0.0};
     if (live) {
@@ -206,7 +207,7 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
 #pragma unroll 2
                     for (; q < qe; ++q) {
                         const Coef ct = load_record(&srec[buf][q * FO1_REC]);
-                        rk4_mode(ct, kval, h, hh, h6, x, v);
+                        rk4_mode(ct, k2, h, hh, h6, x, v);
                     }
                     --q;                                  // the for statement steps to qe
                     if (qe < cnt) nxt = load_record(&srec[buf][qe * FO1_REC]);
@@ -227,7 +228,7 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
                     __stcs(prow + XO * op, make_double2(x[0], x[1]));
                     __stcs(prow + (XO + 1) * op, make_double2(v[0], v[1]));
                 }
-                if (n + 1 < a.T) rk4_mode(cf, kval, h, hh, h6, x, v);
+                if (n + 1 < a.T) rk4_mode(cf, k2, h, hh, h6, x, v);
             } else if (live) {
                 // ---- regime 2: some modes of the CTA have started, some have not
                 if (n < ts) {
@@ -260,7 +261,7 @@ __device__ __forceinline__ void fo1_consume(const FoArgs& a, int64_t cta, int nt
                         __stcs(prow + XO * op, make_double2(x[0], x[1]));
                         __stcs(prow + (XO + 1) * op, make_double2(v[0], v[1]));
                     }
-                    if (n + 1 < a.T) rk4_mode(cf, kval, h, hh, h6, x, v);
+                    if (n + 1 < a.T) rk4_mode(cf, k2, h, hh, h6, x, v);
                 }
             }
             if (out) {
@@ -403,7 +404,8 @@ __device__ __forceinline__ void fo1_produce(const FoArgs& a, const ProdArgs& f) 
             const double invH2 = 1.0 / (H * H);
             double* r = f.rec + n * FO1_REC;
             r[3 * s + 0] = U * invH2;
-            r[3 * s + 1] = 1.0 / (sf * H);
+            const double rr = 1.0 / (sf * H);
+            r[3 * s + 1] = rr * rr;
             r[3 * s + 2] = (d2U[0] + pd * dU[0] + dU[0] * pd + pd * pd * U) * invH2;   // :667-674
             if (s == 0) { r[12] = phi; r[13] = pd; r[14] = H; r[15] = 0.0; }
         }

@@ -36,7 +36,7 @@ __device__ __forceinline__ void store_row(double* rowbase, int64_t kk, int part,
     }
 }
 
-// kv = -(A v + (kR)^2 x + C x)        cosmomodels.py:663-674
+// kv = -(A v + k^2 R2 x + C x)        cosmomodels.py:663-674   (callers pass kval = k^2)
 // Every coefficient is a broadcast shared-memory load.  With one load per DFMA the LSU (one
 // broadcast wavefront per clock per SM) would cap the fp64 pipe (two warp-DFMAs per clock per
 // SM) at ~50 %, so for even NF the 16-byte aligned rows of C are read as 128-bit pairs.
@@ -52,8 +52,7 @@ __device__ __forceinline__ void mode_rhs(const double* __restrict__ cs, double k
     } else {
         A = cs[0]; R = cs[1];
     }
-    const double kr = kval * R;
-    const double B = kr * kr;
+    const double B = kval * R;                        // kval = k^2, R = 1/(aH)^2
     // column-by-column accumulation: the NF row sums are independent dependency chains and are
     // advanced together (ILP = NF*NC), instead of finishing one row's NF-long chain at a time
     double acc[NF][NC];
@@ -121,8 +120,7 @@ struct FactStage {
             for (int i = 0; i < 5; ++i) hd[i] = lds_one(cs + i);
         }
         A = hd[0];
-        const double kr = kval * hd[1];
-        Bd = fma(kr, kr, hd[2]);
+        Bd = fma(kval, hd[1], hd[2]);                 // kval = k^2, hd[1] = 1/(aH)^2
         double sp[2][NC], sg[2][NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) { sp[0][c] = sp[1][c] = sg[0][c] = sg[1][c] = 0.0; }
@@ -350,7 +348,8 @@ __device__ __forceinline__ void fo_consume(const FoArgs& a, int64_t bx, int j, c
         if (nchunks > 1) issue(1);
     }
 
-    const double kval = live ? a.k[kk] : 0.0;
+    const double kmode = live ? a.k[kk] : 0.0;
+    const double kval = kmode * kmode;                // k^2: the records hold 1/(aH)^2
     const int64_t ts = live ? a.tsix[kk] : INT64_MAX;
     const double h = a.h, hh = h * 0.5, h6 = h / 6.0;   // rk4.py:31-32
     const double nan = qnan();

@@ -27,13 +27,13 @@ __device__ __forceinline__ void bg_rhs(const double* __restrict__ p, const doubl
 }
 
 // One (step n, stage s) entry of a step record from the RK4 stage argument `y` of the background:
-// A = U/H^2, R = 1/(aH), C = M/H^2 (cosmomodels.py:637-674); stage 0 also stores the background
+// A = U/H^2, R2 = 1/(aH)^2, C = M/H^2 (cosmomodels.py:637-674); stage 0 also stores the background
 // row itself, stage 3 the padding word.  Layout: include/pyflation_b200.h (pf_stage_table).
 //
 // `factored` (PF_REC_FACTORED, nflation with nf >= 5 only): nflation's Hessian is m^2 * identity
 // (cmpotentials.py:840), so  M = m^2 I + p g^T + g p^T + U p p^T  with p = phi', g = dU: a scalar
 // diagonal plus a symmetric rank-2 term.  The stage slot then holds the factors instead of the
-// dense matrix:  A, R, d = m^2/H^2, U, 1/H^2, 0, p[NF], g[NF]  (6 + 2 NF <= 2 + NF^2 doubles), and the
+// dense matrix:  A, R2, d = m^2/H^2, U, 1/H^2, 0, p[NF], g[NF]  (6 + 2 NF <= 2 + NF^2 doubles), and the
 // mode kernel forms  C x = d x + p (g.x + U p.x)/H^2 + g (p.x)/H^2  in 4 NF + 3 FMAs instead of NF^2.
 template <int POT, int NF>
 __device__ __forceinline__ void stage_record(const double* __restrict__ par, double ainit,
@@ -52,7 +52,8 @@ __device__ __forceinline__ void stage_record(const double* __restrict__ par, dou
     const double invH2 = 1.0 / (H * H);
     double* o = r + s * SW;
     o[0] = U * invH2;                                     // A  (:673  U*y'/H**2)
-    o[1] = 1.0 / (a * H);                                 // R  (:673  k/(a*H))
+    const double rr = 1.0 / (a * H);
+    o[1] = rr * rr;                                       // R2 = 1/(aH)^2  (:673  (k/(a*H))**2)
     bool dense = true;
     if constexpr (POT == PF_NFLATION && NF >= 5) {
         if (factored) {

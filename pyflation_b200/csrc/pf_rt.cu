@@ -8,7 +8,7 @@
 // per mode-step, same mathematics, same output layout.
 //
 //   bg_rt_kernel          K1   serial RK4 of (phi_i, phi'_i, H), NumPy's rounding (-fmad=false)
-//   stage_table_rt_kernel K1b  factored records: A, R, d, U, 1/H^2, 0, p[nf], g[nf] per stage
+//   stage_table_rt_kernel K1b  factored records: A, R2, d, U, 1/H^2, 0, p[nf], g[nf] per stage
 //   fo_rt_kernel          K3   thread <-> (k, j, re|im): x' = v, v' = -(A v + ((kR)^2 + d) x + p w + g z)
 //   potential_rt / derivs_rt   K0 / K8 for API completeness
 #include "pf_common.cuh"
@@ -109,7 +109,8 @@ __global__ void stage_table_rt_kernel(double mass, int nf, double ainit, int64_t
     const double H = y[2 * nf];
     const double invH2 = 1.0 / (H * H);
     o[0] = U * invH2;                                     // A
-    o[1] = 1.0 / (a * H);                                 // R
+    const double rr = 1.0 / (a * H);
+    o[1] = rr * rr;                                       // R2 = 1/(aH)^2
     o[2] = m2 * invH2;                                    // d
     o[3] = U;
     o[4] = invH2;
@@ -127,8 +128,7 @@ struct StageRt {
     const double* g;
     __device__ __forceinline__ void prepare(const double* __restrict__ cs, int nf, double kval, const double* xin) {
         A = __ldg(cs);
-        const double kr = kval * __ldg(cs + 1);
-        Bd = fma(kr, kr, __ldg(cs + 2));
+        Bd = fma(kval, __ldg(cs + 1), __ldg(cs + 2));   // kval = k^2, record holds 1/(aH)^2
         const double U = __ldg(cs + 3), invH2 = __ldg(cs + 4);
         p = cs + 6;
         g = cs + 6 + nf;
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(128) fo_rt_kernel(FoArgs a, int nf) {
     const int64_t kk = (int64_t)blockIdx.x * (blockDim.x >> 1) + kl;
     if (kk >= a.nk) return;
     const int64_t nk = a.nk, op = a.opitch;
-    const double kval = a.k[kk];
+    const double kval = a.k[kk] * a.k[kk];
     const int64_t ts = a.tsix[kk];
     const double h = a.h, hh = h * 0.5, h6 = h / 6.0;     // rk4.py:31-32
     const double nan = qnan();
