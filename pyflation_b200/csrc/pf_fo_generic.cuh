@@ -306,7 +306,7 @@ __device__ __forceinline__ void rk4_step(const double* __restrict__ r, double kv
 template <int NF, int NC, bool FACT = false>
 __device__ __forceinline__ void fo_consume(const FoArgs& a, int64_t bx, int j, const long long* progress) {
     using S = FoShape<NF>;
-    constexpr int NB = S::NB, SW = S::SW, REC = S::REC, CH = S::CH;
+    constexpr int NB = S::NB, REC = S::REC, CH = S::CH;
     const bool pert = a.layout == PF_LAYOUT_PERT;     // perturbation rows only
     const int NV = pert ? 2 * NF * NF : nvar_of(NF);
     const int RO = pert ? -NB : 0;                    // row offset of the perturbation block
