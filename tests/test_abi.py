@@ -152,3 +152,35 @@ def test_host_fill_background_on_cpu(nf, pert_nan, sorted_starts):
     assert np.all(out[:10] == 7.0 + 7.0j) and np.all(out[20:] == 7.0 + 7.0j)
     assert np.array_equal(out[10:20].view(np.float64), want[10:20].view(np.float64), equal_nan=True)
     assert L.pf_host_fill_background(None, nf, nk, 0, T, None, rec_len, bg_off, None, None, 0, 1) == -1
+
+
+def test_peer_and_probe_entries_reject_bad_arguments():
+    """Argument checks of the round-2 entry points that need no GPU to fail."""
+    from pyflation_b200 import _lib
+    L = _lib.lib()
+    buf = ctypes.create_string_buffer(_lib.PF_PEER_HANDLE_BYTES)
+    p = ctypes.c_void_p()
+    assert L.pf_peer_alloc(0, ctypes.byref(p)) == -1
+    assert L.pf_peer_alloc(16, None) == -1
+    assert L.pf_peer_export(None, buf) == -1
+    assert L.pf_peer_open(None, ctypes.byref(p)) == -1
+    assert L.pf_peer_open(buf.raw, None) == -1
+    assert L.pf_peer_free(None) == 0 and L.pf_peer_close(None) == 0
+    out = ctypes.c_double(0.0)
+    assert L.pf_fp64_peak_probe(0, None, 0, ctypes.byref(out)) == -1
+    assert b"pf_fp64_peak_probe" in L.pf_last_error()
+    # record layout helpers: compiled instantiations hold the dense matrix, runtime-nf the factors
+    assert int(L.pf_rec_doubles(1)) == 16 and int(L.pf_rec_bg_offset(1)) == 12
+    assert int(L.pf_rec_doubles(8)) == 282 and int(L.pf_rec_bg_offset(8)) == 264
+    assert int(L.pf_rec_bg_offset(10)) == 4 * (6 + 20) and int(L.pf_rec_doubles(10)) == 126
+    m = _lib.PfModel()
+    m.potential_id, m.nfields = 12, 65                       # nflation takes 1..64 fields
+    assert L.pf_fo_run(ctypes.byref(m), 1, None, None, None, None, 10, 0.01, 0, 10, None, None, 0, 0, 0,
+                       None, None) == -3
+    m.potential_id, m.nfields = 10, 9                        # any other potential: 1..8 / its own nf
+    assert L.pf_fo_run(ctypes.byref(m), 1, None, None, None, None, 10, 0.01, 0, 10, None, None, 0, 0, 0,
+                       None, None) in (-2, -3)
+    # out_pitch smaller than the batch is refused
+    m.potential_id, m.nfields = 0, 1
+    assert L.pf_fo_run(ctypes.byref(m), 8, None, None, None, None, 10, 0.01, 0, 10, None, None, 0, 0, 4,
+                       None, None) == -1
