@@ -246,6 +246,65 @@ def test_unsorted_start_rows_through_the_compact_host_path():
         assert mode_rel_err(dev, base[:, :, perm], nf) < 1e-12
 
 
+@pytest.mark.parametrize("name,nk", [("c2_lambdaphi4_2p16", 16411), ("c2_lambdaphi4_2p16", 333),
+                                     ("c3_hybridquadratic_2p20", 301), ("nflation5", 97), ("nflation10", 37)])
+def test_kernels_stay_inside_their_buffers(name, nk):
+    """compute-sanitizer is not available on the GPU pool, so the bounds check is our own: every
+    buffer a mode kernel writes (trajectory, carried state, solve scratch) sits between guard
+    bands of a sentinel, for full / strided / windowed / pitched launches (fused, plain, lock-step,
+    factored and runtime-nfields kernels), and the guards must come back untouched."""
+    import torch
+    from pyflation_b200 import engine
+    g = load_fo(name)
+    nf = g["nfields"]
+    m, prob = _problem(g, k=np.linspace(KMIN, KMAX, nk))
+    T, nvar = prob.T, prob.nvar
+    y0, n0 = np.real(m.foystart[0:2 * nf + 1, 0]).copy(), int(m.fotstartindex.min())
+    GUARD, SENT = 8192, -7.25
+
+    def guarded(n_complex):
+        big = torch.full((n_complex + 2 * GUARD,), SENT, dtype=torch.complex128, device="cuda")
+        return big, big[GUARD:GUARD + n_complex]
+
+    def intact(big):
+        return bool((big[:GUARD] == SENT).all()) and bool((big[-GUARD:] == SENT).all())
+
+    # carried state and solve scratch behind guards as well
+    sbig, sview = guarded(2 * nf * nf * nk)
+    sview.zero_()
+    prob.state = sview.view(2 * nf * nf, nk)
+    nscr = int(__import__("pyflation_b200")._lib.lib().pf_solve_scratch_doubles(nf, T))
+    cbig, cview = guarded((nscr + 1) // 2)
+    prob.scratch = torch.view_as_real(cview).reshape(-1)[:nscr]
+    cases = [("solve full", dict(every=1, t0=None)), ("solve every 7", dict(every=7, t0=None)),
+             ("window", dict(every=1, t0=T // 2, t1=T // 2 + 1100)), ("tail window", dict(every=1, t0=T - 37, t1=T)),
+             ("pitched", dict(every=5, t0=None, pitch=nk + 13))]
+    for label, c in cases:
+        every, pitch = c["every"], c.get("pitch", 0)
+        width = pitch or nk
+        if c["t0"] is None:
+            rows = (T + every - 1) // every
+            big, view = guarded(rows * nvar * width)
+            prob.rec_ready = False
+            prob.solve(y0, n0, T, view, every, out_pitch=pitch)
+        else:
+            prob.launch(0, c["t0"], None, 0)                     # state at t0 (records exist by now)
+            rows = c["t1"] - c["t0"]
+            big, view = guarded(rows * nvar * width)
+            prob.launch(c["t0"], c["t1"], view, 1)
+        torch.cuda.synchronize()
+        prob.check_flags()
+        assert intact(big), label + ": trajectory guard band overwritten"
+        assert intact(sbig), label + ": state guard band overwritten"
+        assert intact(cbig), label + ": scratch guard band overwritten"
+        out = view.view(rows, nvar, width)
+        if pitch:
+            assert bool((out[:, :, nk:] == SENT).all()), "columns beyond nk touched"
+        # every cell of the batch's own columns was written (NaN or a number, never the sentinel)
+        assert not bool((torch.view_as_real(out[:, :, :nk])[..., 0] == SENT).any()), label + ": unwritten cells"
+        del big, view, out
+
+
 def test_fused_solve_equals_separate_kernels():
     """pf_fo_solve (producer CTA + consumers in one launch, nf = 1) against the three-kernel
     sequence pf_bg_run / pf_stage_table / pf_fo_run, and its windowed continuation."""
