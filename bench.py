@@ -425,7 +425,7 @@ def measure_config5(world, rank, barrier):
             t0 = time.perf_counter()
             r = parallel.sharded_spectrum_run("msqphisq", k, gather=True, **kw)
             if tag == "e2e_spectrum":
-                pr_host = r["scaled_Pr_all"][-1].cpu().numpy()
+                pr_host = parallel.to_host(r["scaled_Pr_all"][-1])
             torch.cuda.synchronize()
             barrier()
             walls.append(time.perf_counter() - t0)
@@ -481,13 +481,15 @@ def measure_collective(world, rank, barrier):
         got = full[torch.as_tensor(sel // every, device=full.device)][:, :, torch.as_tensor(g["kix"], device=full.device)]
         got = got.cpu().numpy()
         want = g["yrows"][np.isin(g["rows"], sel)]
-        assert np.array_equal(np.isnan(got), np.isnan(want)), "NaN layout differs from the golden columns"
+        # no exception here: a rank that left this function early would desynchronise the
+        # collectives that follow; the verdict is recorded and raised after the JSON line is out
+        if not np.array_equal(np.isnan(got), np.isnan(want)):
+            return float("inf")
         fin = ~np.isnan(want)
-        scale = np.nanmax(np.abs(want[:, 3:]), axis=1, keepdims=True) * np.ones_like(want.real)
+        with np.errstate(invalid="ignore"):
+            scale = np.nanmax(np.abs(want[:, 3:]), axis=1, keepdims=True) * np.ones_like(want.real)
         scale[:, :3] = np.abs(want[:, :3])
-        err = float((np.abs(got[fin] - want[fin]) / scale[fin]).max())
-        assert err < 1e-9, "gathered columns differ from the reference golden columns: %.3e" % err
-        return err
+        return float((np.abs(got[fin] - want[fin]) / scale[fin]).max())
 
     def timed(fn):
         barrier()
@@ -520,6 +522,9 @@ def measure_collective(world, rank, barrier):
         out["parity_fused_max_rel_err"] = check(full_b)
     del full_b
     asm.close()
+    if rank == 0:
+        out["parity_tolerance"] = 1e-9
+        out["parity_ok"] = bool(out["parity_nccl_max_rel_err"] < 1e-9 and out["parity_fused_max_rel_err"] < 1e-9)
     moved = nbytes * (world - 1) / world                       # bytes that cross NVLink into rank 0
     out.update({"ms_compute_only": ms_local, "ms_nccl_allgather_path": ms_nccl, "ms_fused_peer_store_path": ms_fused,
                 "nvlink_bytes_into_root": moved,
@@ -659,17 +664,30 @@ def run_gpu_arm(args):
     # ---- the other BASELINE configurations, config 5, the collective
     extras = {}
     if not args.no_extras:
-        fp64_peak = engine.fp64_peak_tflops()
-        extras["fp64_peak_tflops"] = fp64_peak
-        if world == 1:
-            extras["configs"] = measure_extra_configs(peak, fp64_peak, device_index=local_rank)
-            extras["configs"].append(measure_window_config(peak, fp64_peak, device_index=local_rank))
-        extras.update(measure_config5(world, rank, barrier))
-        if world > 1:
-            extras["collective"] = measure_collective(world, rank, barrier)
+        try:
+            fp64_peak = engine.fp64_peak_tflops()
+            extras["fp64_peak_tflops"] = fp64_peak
+            if world == 1:
+                extras["configs"] = measure_extra_configs(peak, fp64_peak, device_index=local_rank)
+                extras["configs"].append(measure_window_config(peak, fp64_peak, device_index=local_rank))
+            extras.update(measure_config5(world, rank, barrier))
+            if world > 1:
+                extras["collective"] = measure_collective(world, rank, barrier)
+        except Exception as err:                         # the headline line must still come out
+            import traceback
+            extras["extras_error"] = repr(err)
+            traceback.print_exc(file=sys.stderr)
+            torch.cuda.empty_cache()
 
     # ---- e2e through the public API with host buffers
-    e2e = None if args.no_e2e else run_e2e(args, m, T, nvar, mode_steps, world, rank, barrier)
+    e2e = None
+    if not args.no_e2e:
+        try:
+            e2e = run_e2e(args, m, T, nvar, mode_steps, world, rank, barrier)
+        except Exception as err:                             # the headline line must still come out
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            e2e = {"error": repr(err)}
 
     if rank == 0:
         line = {
@@ -682,7 +700,12 @@ def run_gpu_arm(args):
             "T": T, "mode_steps_per_gpu_step": mode_steps,
         }
         line.update(extras)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+        coll = extras.get("collective")
+        if coll is not None and coll.get("parity_ok") is False:
+            raise SystemExit("bench: the assembled yresult differs from the reference's golden columns "
+                             "(nccl %.3e, fused %.3e)" % (coll["parity_nccl_max_rel_err"],
+                                                          coll["parity_fused_max_rel_err"]))
     if world > 1:
         dist.destroy_process_group()
 

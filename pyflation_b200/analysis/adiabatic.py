@@ -59,15 +59,9 @@ def _pr_on_device(y, nfields, chunk_bytes=512 << 20):
 
 
 def _to_host(block):
-    """Device block -> fresh NumPy array through a page-locked staging tensor (torch's caching
-    pinned allocator makes repeated calls cheap; the array keeps the staging block alive)."""
-    import torch
-    try:
-        host = torch.empty(block.shape, dtype=block.dtype, pin_memory=True)
-    except RuntimeError:
-        host = torch.empty(block.shape, dtype=block.dtype)
-    host.copy_(block)
-    return host.numpy()
+    """Device block -> fresh NumPy array through a page-locked staging tensor."""
+    from ..parallel import to_host
+    return to_host(block)
 
 
 def _slices(m, tix, kix):

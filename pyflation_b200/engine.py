@@ -522,7 +522,18 @@ def spectrum_run(potential_func, k, nfields=1, pot_params=None, bgystart=None, c
     m = c.FOCanonicalTwoStage(k=np.array([1e-60]), potential_func=potential_func,
                               pot_params=pot_params, nfields=nf, bgystart=bgystart, cq=cq,
                               tend=tend, tstep_wanted=h, simtstart=simtstart)
+    import time
+    timing = {} if os.environ.get("PF_SPECTRUM_TIMING") else None
+
+    def lap(name, t0):
+        if timing is not None:
+            torch.cuda.synchronize()
+            timing[name] = timing.get(name, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
+
+    t0 = time.perf_counter()
     m.runbg()
+    t0 = lap("runbg", t0)
     if fixed_ainit is None:
         ainit = float(np.ravel(m._choose_ainit())[0])
     else:
@@ -535,8 +546,10 @@ def spectrum_run(potential_func, k, nfields=1, pot_params=None, bgystart=None, c
         kd = k.to(dev, torch.float64).contiguous() if torch.is_tensor(k) else \
             torch.as_tensor(np.ascontiguousarray(k, dtype=np.float64)).to(dev)
         bg = torch.as_tensor(np.ascontiguousarray(bgy)).to(dev)
+        t0 = lap("h2d", t0)
         rows0, ystart = device_initial_conditions(kd, bg, int(m.fotendindex), nf, ainit, etainit, cq,
                                                   simtstart, h, phase, suppress_ix)
+        t0 = lap("initial_conditions", t0)
         n0 = int(rows0.min().item())
         if int(rows0[0].item()) != n0:
             raise ValueError("k must be sorted so that column 0 starts first (cosmomodels.py:641)")
@@ -544,13 +557,16 @@ def spectrum_run(potential_func, k, nfields=1, pot_params=None, bgystart=None, c
         prob = FirstOrderProblem(pm, kd, rows0, ystart, simtstart, T, h, dev)
         stride = max(1, T - 1) if row_stride == "last" else int(row_stride)
         y0 = bgy[n0].copy()
+        t0 = lap("problem_setup", t0)
         out = first_order_device(prob, out_every=stride, y0=y0, n0=n0)
         prob.check_flags()
+        t0 = lap("integration", t0)
         pr = pr_spectrum_device(nf, out)
         spr = pr_spectrum_device(nf, out, kd)
+        t0 = lap("P_R", t0)
     tres = (simtstart + np.arange(T) * h)[::stride]
     return dict(k=kd, fotstartindex=rows0, rows=out, tresult=tres, Pr=pr, scaled_Pr=spr, ainit=ainit,
-                etainit=etainit, fotend=m.fotend, fotendindex=int(m.fotendindex), T=T)
+                etainit=etainit, fotend=m.fotend, fotendindex=int(m.fotendindex), T=T, timing=timing)
 
 
 def fp64_peak_tflops(iters=100000, device=None):

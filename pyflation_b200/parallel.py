@@ -269,6 +269,18 @@ class ShardedFirstOrder(object):
         return (asm.tensor() if asm.owner else None), asm
 
 
+def to_host(t):
+    """Device tensor -> NumPy array through a page-locked staging tensor (torch's caching pinned
+    allocator keeps repeated calls cheap; a pageable ``.cpu()`` of a 2^25-mode spectrum costs
+    more than the integration of a rank's slab)."""
+    try:
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    except RuntimeError:
+        host = torch.empty(t.shape, dtype=t.dtype)
+    host.copy_(t)
+    return host.numpy()
+
+
 def sharded_spectrum_run(potential_func, k, gather=True, **kwargs):
     """BASELINE config 5: a k grid of 2^20..2^24 modes sharded over the ranks of the process
     group.  Each rank runs the device-resident pipeline (engine.spectrum_run) on its contiguous
