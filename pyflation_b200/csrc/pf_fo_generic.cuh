@@ -20,9 +20,6 @@ struct FoShape {
     static constexpr int BLOCK = PF_FO_BLOCK;
 };
 
-template <class T>
-__device__ __forceinline__ void plain_store(T* p, T v) { *p = v; }
-
 // one complex (NC = 2) or one real component (NC = 1) per row, per thread
 template <int NC>
 __device__ __forceinline__ void store_row(double* rowbase, int64_t kk, int part, const double (&c)[NC]) {
