@@ -51,18 +51,21 @@ __device__ __forceinline__ void mode_rhs(const double* __restrict__ cs, double k
     }
     const double B = kval * R;                        // kval = k^2, R = 1/(aH)^2
     // column-by-column accumulation: the NF row sums are independent dependency chains and are
-    // advanced together (ILP = NF*NC), instead of finishing one row's NF-long chain at a time
+    // advanced together (ILP = NF*NC), instead of finishing one row's NF-long chain at a time.
+    // k^2 R2 is folded into the diagonal of C (one add per row) instead of one FMA per element.
     double acc[NF][NC];
 #pragma unroll
     for (int i = 0; i < NF; ++i)
 #pragma unroll
-        for (int c = 0; c < NC; ++c) acc[i][c] = fma(B, x[i][c], A * v[i][c]);
+        for (int c = 0; c < NC; ++c) acc[i][c] = A * v[i][c];
     if constexpr (NF % 2 == 0) {
 #pragma unroll
         for (int l = 0; l < NF / 2; ++l) {
 #pragma unroll
             for (int i = 0; i < NF; ++i) {
-                const double2 cc = reinterpret_cast<const double2*>(cs + 2 + i * NF)[l];
+                double2 cc = reinterpret_cast<const double2*>(cs + 2 + i * NF)[l];
+                if (2 * l == i) cc.x += B;
+                if (2 * l + 1 == i) cc.y += B;
 #pragma unroll
                 for (int c = 0; c < NC; ++c) acc[i][c] = fma(cc.x, x[2 * l][c], acc[i][c]);
 #pragma unroll
@@ -74,7 +77,8 @@ __device__ __forceinline__ void mode_rhs(const double* __restrict__ cs, double k
         for (int l = 0; l < NF; ++l)
 #pragma unroll
             for (int i = 0; i < NF; ++i) {
-                const double cc = cs[2 + i * NF + l];
+                double cc = cs[2 + i * NF + l];
+                if (l == i) cc += B;
 #pragma unroll
                 for (int c = 0; c < NC; ++c) acc[i][c] = fma(cc, x[l][c], acc[i][c]);
             }
