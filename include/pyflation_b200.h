@@ -224,6 +224,11 @@ int pf_pr_spectrum_pert(int nfields, int64_t nrows, int64_t nk, const double *pe
  * picks the hardware concurrency. */
 int pf_copy_rows_d2h(void *dst_host, size_t dst_pitch, const void *src_dev, size_t src_pitch,
                      size_t width_bytes, size_t height, void *stream);
+/* A whole device window window_dev c128 [nt][wrows][nk] into yresult_host c128 [T][nvar][nk] at
+ * variable rows [row0, row0 + wrows) of time steps [t0, t0 + nt), columns [0, kcols) only: ONE
+ * asynchronous 3-D copy (instead of one pitched copy per variable row), no pitch limit. */
+int pf_copy_window_d2h(void *yresult_host, int64_t nvar, int64_t nk, int64_t row0, int64_t t0,
+                       const void *window_dev, int64_t wrows, int64_t kcols, int64_t nt, void *stream);
 int pf_host_fill_background(double *yout_host, int nfields, int64_t nk, int64_t t0, int64_t t1,
                             const double *bg_host, int64_t bg_pitch, int64_t bg_off,
                             const int64_t *tsix_host, const double *ystart_host, int pert_nan,

@@ -24,7 +24,7 @@ EXPORTS = [
     "pf_potential_nfields", "pf_potential_nparams", "pf_potential_param_name",
     "pf_potential_param_default", "pf_potential_eval", "pf_number_of_steps", "pf_nvar",
     "pf_rec_doubles", "pf_rec_bg_offset", "pf_bg_run", "pf_stage_table", "pf_fo_run", "pf_solve_scratch_doubles",
-    "pf_fo_solve", "pf_pr_spectrum", "pf_pr_spectrum_pert", "pf_scatter_slab", "pf_copy_rows_d2h",
+    "pf_fo_solve", "pf_pr_spectrum", "pf_pr_spectrum_pert", "pf_scatter_slab", "pf_copy_rows_d2h", "pf_copy_window_d2h",
     "pf_host_fill_background", "pf_crossing_rows", "pf_bunch_davies", "pf_derivs",
     "pf_fp64_peak_probe", "pf_peer_alloc", "pf_peer_free", "pf_peer_export", "pf_peer_open", "pf_peer_close",
 ]
@@ -95,6 +95,7 @@ def lib():
                               c_dbl, c_i64, c_vp, c_vp, c_vp, c_i64, ctypes.c_int32, c_i64, c_vp, c_vp]
     c_sz = ctypes.c_size_t
     L.pf_copy_rows_d2h.argtypes = [c_vp, c_sz, c_vp, c_sz, c_sz, c_sz, c_vp]
+    L.pf_copy_window_d2h.argtypes = [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp]
     L.pf_host_fill_background.argtypes = [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64,
                                           c_vp, c_vp, c_int, c_int]
     L.pf_pr_spectrum.argtypes = [c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]

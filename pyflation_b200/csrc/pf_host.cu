@@ -160,6 +160,26 @@ extern "C" int pf_copy_rows_d2h(void* dst_host, size_t dst_pitch, const void* sr
     return PF_OK;
 }
 
+extern "C" int pf_copy_window_d2h(void* yresult_host, int64_t nvar, int64_t nk, int64_t row0, int64_t t0,
+                                  const void* window_dev, int64_t wrows, int64_t kcols, int64_t nt,
+                                  void* stream) {
+    if (nt == 0 || kcols == 0 || wrows == 0) return PF_OK;
+    if (!yresult_host || !window_dev || nvar < 1 || nk < 1 || row0 < 0 || t0 < 0 || wrows < 0 ||
+        row0 + wrows > nvar || kcols < 0 || kcols > nk || nt < 0) {
+        set_error("pf_copy_window_d2h: bad arguments");
+        return PF_E_ARG;
+    }
+    // one 3-D copy: x = started columns (bytes), y = the window's variable rows, z = time steps
+    cudaMemcpy3DParms p = {};
+    p.srcPtr = make_cudaPitchedPtr(const_cast<void*>(window_dev), (size_t)nk * 16, (size_t)nk * 16, (size_t)wrows);
+    p.dstPtr = make_cudaPitchedPtr(yresult_host, (size_t)nk * 16, (size_t)nk * 16, (size_t)nvar);
+    p.dstPos = make_cudaPos(0, (size_t)row0, (size_t)t0);
+    p.extent = make_cudaExtent((size_t)kcols * 16, (size_t)wrows, (size_t)nt);
+    p.kind = cudaMemcpyDeviceToHost;
+    PF_CUDA_CHECK(cudaMemcpy3DAsync(&p, (cudaStream_t)stream), "pf_copy_window_d2h");
+    return PF_OK;
+}
+
 extern "C" int pf_host_fill_background(double* yout_host, int nfields, int64_t nk, int64_t t0, int64_t t1,
                                        const double* bg_host, int64_t bg_pitch, int64_t bg_off,
                                        const int64_t* tsix_host, const double* ystart_host, int pert_nan,

@@ -330,9 +330,6 @@ def first_order_host(prob, out=None, slab_bytes=1 << 30, ring=None, y0=None, n0=
     npert = nvar - nb
     compact = bool(compact and ring is None and prob.tsix_host is not None
                    and prob.ystart_host is not None)
-    # cudaMemcpy2D pitches stop at 2 GiB: very wide rows take the full-row copies
-    if compact and nvar * nk * 16 >= (1 << 31):
-        compact = False
     rows_per_t = npert if compact else nvar
     W = plan_window(T, rows_per_t, nk, slab_bytes)
     if ring is not None:
@@ -382,21 +379,16 @@ def first_order_host(prob, out=None, slab_bytes=1 << 30, ring=None, y0=None, n0=
                 done.record(compute)
                 copier.wait_event(done)
                 with torch.cuda.stream(copier):
-                    if compact and sorted_starts:
-                        kcols = int(np.searchsorted(prob.tsix_host, t1 - 1, side="right"))
+                    if compact:
+                        # perturbation rows of the window, started columns only when the start
+                        # rows are sorted in k, straight into rows [2nf+1, nvar) of the result:
+                        # one 3-D copy per window
+                        kcols = int(np.searchsorted(prob.tsix_host, t1 - 1, side="right")) \
+                            if sorted_starts else nk
                         d2h_bytes += npert * kcols * 16 * (t1 - t0)
-                        for r in range(npert if kcols else 0):       # one pitched copy per variable row
-                            dst = out.data_ptr() + ((t0 * nvar + nb + r) * nk) * 16
-                            _lib.check(L.pf_copy_rows_d2h(ctypes.c_void_p(dst), nvar * nk * 16,
-                                                          ctypes.c_void_p(slabs[b].data_ptr() + r * nk * 16),
-                                                          npert * nk * 16, kcols * 16, t1 - t0,
-                                                          _stream_ptr(copier)))
-                    elif compact:
-                        d2h_bytes += npert * nk * 16 * (t1 - t0)
-                        dst = out.data_ptr() + (t0 * nvar + nb) * nk * 16
-                        _lib.check(L.pf_copy_rows_d2h(ctypes.c_void_p(dst), nvar * nk * 16, _ptr(slabs[b]),
-                                                      npert * nk * 16, npert * nk * 16, t1 - t0,
-                                                      _stream_ptr(copier)))
+                        _lib.check(L.pf_copy_window_d2h(ctypes.c_void_p(out.data_ptr()), nvar, nk, nb, t0,
+                                                        _ptr(slabs[b]), npert, kcols, t1 - t0,
+                                                        _stream_ptr(copier)))
                     else:
                         d2h_bytes += nvar * nk * 16 * (t1 - t0)
                         dst = out[t0:t1] if ring is None else ring[(w % 2) * W:(w % 2) * W + (t1 - t0)]
