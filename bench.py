@@ -408,6 +408,71 @@ def measure_window_config(hbm_peak, fp64_peak, reps=3, device_index=0):
         return {"workload": name, "error": repr(err)}
 
 
+def measure_second_order(hbm_peak, reps=3, device_index=0):
+    """the second-order stage (K9, pf_so_run) on the headline grid -- lambdaphi4,
+    2^16 modes, CanonicalRampedSecondOrder, full (T/2, 4, nk) float64 trajectory left in HBM, with a
+    synthetic source term (T, nk) complex128 resident in HBM (computing it is out of scope).
+    HBM-bound: 32 B of source read + 32 B of result written per mode and second-order step."""
+    import torch
+    from pyflation_b200 import cosmomodels, engine
+    name = "second order (8f-4): lambdaphi4, 2^16 modes, ramped source, full trajectory (8.2 GB in, 8.2 GB out)"
+    try:
+        nk = 2 ** 16
+        k = np.linspace(KMIN, KMAX, nk)
+        m = cosmomodels.FOCanonicalTwoStage(k=k, potential_func="lambdaphi4", pot_params={"nfields": 1}, nfields=1,
+                                            bgystart=np.array([25.0, 0.0, 0.0]), cq=CQ, tend=TEND, tstep_wanted=H)
+        m.runbg()
+        m.setfoics()
+        T_fo = int(np.around(m.fotend / H) + 1)
+        h2 = 2 * H
+        tsix = np.around(m.fotstartindex * 0.5 + h2 / 2).astype(np.int64)          # cosmomodels.py:1706-1709
+        T = int(np.around((T_fo - 1) * H / h2) + 1)
+        pm = engine.make_model("lambdaphi4", {"nfields": 1}, 1, m.ainit)
+        tt = torch.arange(T_fo, dtype=torch.float64, device="cuda")[:, None] * H
+        kk = torch.as_tensor(k, device="cuda")[None, :]
+        amp = (kk / 1e-60) ** -1.5 * torch.exp(-0.08 * tt)
+        src = torch.complex(amp * torch.cos(0.9 * tt + 3.0 * (kk / 1e-58)), amp * torch.sin(1.3 * tt + 0.5))
+        del amp
+        ramp = {"a": 15.0, "b": 0.3, "c": 1, "d": 2, "e": 1}
+        prob = engine.SecondOrderProblem(pm, k, tsix, np.zeros((4, nk)), 0.0, T, h2,
+                                         fo_bg0=m.bgmodel.yresult[:T_fo, :, 0], bgepsilon=m.bgepsilon,
+                                         fo_simtstart=0.0, fo_tstep=H, fo_tsix=m.fotstartindex, source=src,
+                                         ramp=ramp, tstart=m.fotstart)
+        out = torch.empty((T, 4, nk), dtype=torch.float64, device="cuda")
+        prob.launch(0, T, out, 1)
+        torch.cuda.synchronize()
+        sampler = ClockSampler(device_index)
+        sampler.start()
+        ev = _events(reps)
+        for a, b in ev:
+            a.record()
+            prob.launch(0, T, out, 1)
+            b.record()
+        torch.cuda.synchronize()
+        sampler.stop_flag = True
+        sampler.join()
+        ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+        last = out[T - 1]
+        assert bool(torch.isfinite(last).all()) and float(last.abs().max()) > 0
+        mode_steps = float(np.sum(T - 1 - tsix))
+        alg_bytes = mode_steps * 64.0
+        all_bytes = mode_steps * 32.0 + float(T) * nk * 32.0
+        del out, prob, src
+        torch.cuda.empty_cache()
+        return {"workload": name, "nk": nk, "T": T, "value": mode_steps / (ms * 1e-3), "ms": ms,
+                "unit": "k-mode second-order RK4-steps/s", "mode_kernel_ms": ms,
+                "output_policy": "full trajectory", "clocks": sampler.result(),
+                "roofline": {"bound": "hbm", "frac": alg_bytes / (ms * 1e-3) / 1e9 / hbm_peak, "timed": "mode kernel",
+                             "hbm": {"achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": alg_bytes / (ms * 1e-3) / 1e9 / hbm_peak,
+                                     "bytes_per_mode_step": 64,
+                                     "achieved_all_rows": all_bytes / (ms * 1e-3) / 1e9,
+                                     "frac_all_rows": all_bytes / (ms * 1e-3) / 1e9 / hbm_peak}}}
+    except Exception as err:
+        torch.cuda.empty_cache()
+        return {"workload": name, "error": repr(err)}
+
+
 def measure_config5(world, rank, barrier):
     """BASELINE configs[4]: msqphisq, k-sharded, device-resident pipeline.
     strong        : fixed 2^24-mode grid over the N ranks, P_R(k) gathered with NCCL.
@@ -670,6 +735,7 @@ def run_gpu_arm(args):
             if world == 1:
                 extras["configs"] = measure_extra_configs(peak, fp64_peak, device_index=local_rank)
                 extras["configs"].append(measure_window_config(peak, fp64_peak, device_index=local_rank))
+                extras["configs"].append(measure_second_order(peak, device_index=local_rank))
             extras.update(measure_config5(world, rank, barrier))
             if world > 1:
                 extras["collective"] = measure_collective(world, rank, barrier)

@@ -8,6 +8,7 @@
  *     pyflation/cosmomodels.py:625-675 CanonicalFirstOrder.derivs
  *     pyflation/cmpotentials.py:16-1144  the 18 potential functions (U, dU, d2U)
  *     pyflation/analysis/adiabatic.py:153-285  Pr / scaled_Pr (pf_pr_spectrum)
+ *     pyflation/cosmomodels.py:678-971 CanonicalSecondOrder / RampedSecondOrder.derivs (pf_so_run)
  * The reference has no FFI of its own (a Python callable `derivs` is passed to the solver),
  * so the binding a maintainer adds is the ctypes stub shown in INTEGRATION.md; the host-side
  * mirror of the reference's modules that does this lives in pyflation_b200/{rk4,cosmomodels}.py.
@@ -239,6 +240,41 @@ int pf_host_fill_background(double *yout_host, int nfields, int64_t nk, int64_t 
  * column offset k0 (the on-GPU permute after an NCCL all-gather of slabs). */
 int pf_scatter_slab(int64_t nrows_times_nvar, int64_t nk_r, int64_t nk, int64_t k0,
                     const double *slab_dev, double *full_dev, void *stream);
+
+/* ---- K9: second-order perturbation RK4 over a batch of k modes ----
+ * Replaces rkdriver_tsix + rk4stepks driving CanonicalSecondOrder.derivs (cosmomodels.py:708-766)
+ * or CanonicalRampedSecondOrder.derivs (:893-971) as SOCanonicalThreeStage.runso sets them up
+ * (:1680-1790), for rows [t0, t1) of the second-order time grid (step h = 2 x the first-order step).
+ * The state per mode is the real 4-vector (Re d2, Re d2', Im d2, Im d2'):
+ *     y0' = y1,  y1' = -( (3-eps) y1 + (k/(aH))^2 y0 + (V''/H^2 - 3 phi'^2) y0 + Re S )   (same for y2, y3, Im S)
+ *   coef_dev[T][3][PF_SO_COEF]: for step n -> n+1 and its three stage times t = simtstart + n h,
+ *     + h/2, + h (rk4.py:27-55, 116-118):  3 - eps,  1/(a H)^2,  V''/H^2 - 3 phi'^2,  t,
+ *     fotix = around((t - fo_simtstart)/fo_step) (row of the first-order time grid the reference
+ *     reads at this stage, :724), t/h (compared with the start row by the ramp, :935-937);
+ *     eps, H, phi', V'' taken at row fotix of the first-order / background result.
+ *   source_dev c128 [source_rows][source_pitch]: the source term on the first-order time grid,
+ *     column k of this batch at column k; NULL = no source (homogeneous equation).  Every fotix
+ *     in coef_dev must be < source_rows (the caller checks; the reference raises IndexError).
+ *   tsix_dev[nk]: second-order start rows; fo_tsix_dev[nk] (may be NULL): first-order start rows --
+ *     a stage whose fotix lies before a mode's first-order start reads NaN there in the reference
+ *     and poisons the mode; ystart_dev [4][nk].
+ *   ramp_host (may be NULL) = {a, b, c, d, e}: S is multiplied by (tanh(a (t - tstart_k - b)) + c)/d
+ *     while |t - tstart_k - b| < e, and by 0 at the stage with t/h == tsix_k (:925-944);
+ *     tstart_dev[nk] = first-order start times (required with a ramp).
+ *   state_dev [4][nk], yout_dev [rows][4][out_pitch or nk] float64, out_every: as pf_fo_run. */
+#define PF_SO_COEF 6
+int pf_so_run(int64_t nk, const double *k_dev, const int64_t *tsix_dev, const int64_t *fo_tsix_dev,
+              const double *ystart_dev, const double *coef_dev, const double *source_dev,
+              int64_t source_rows, int64_t source_pitch, const double *tstart_dev,
+              const double *ramp_host, int64_t T, double h, int64_t t0, int64_t t1,
+              double *state_dev, double *yout_dev, int64_t out_every, int64_t out_pitch,
+              void *stream);
+/* One right-hand side dydx_dev[4][nk] = derivs(y_dev[4][nk], t): coef_dev[PF_SO_COEF] of that
+ * time, source_row_dev c128 [nk] = source[fotix] (NULL: CanonicalHomogeneousSecondOrder.derivs,
+ * :797-848); tsix_dev may be NULL without a ramp. */
+int pf_so_derivs(int64_t nk, const double *k_dev, const int64_t *tsix_dev, const int64_t *fo_tsix_dev,
+                 const double *y_dev, const double *coef_dev, const double *source_row_dev,
+                 const double *tstart_dev, const double *ramp_host, double *dydx_dev, void *stream);
 
 /* ---- measured fp64 peak (roofline denominator of the compute-bound configurations) ----
  * Runs a DFMA saturation kernel (8 independent chains per thread, 8 x 256 threads per SM) on the

@@ -521,3 +521,88 @@ def first_order_run(potential, k, nf=1, params=None, bgystart=None, cq=50, tend=
                          make_fo_rhs(potential, params, nf, k, ainit))
         out.update(tresult=t, yresult=y)
     return out
+
+
+# --------------------------------------------------------------------------------------
+# second-order stage: rkdriver_tsix driving CanonicalSecondOrder.derivs /
+# CanonicalRampedSecondOrder.derivs (cosmomodels.py:678-766, 850-971) from a first-order result
+# and a given source term, as SOCanonicalThreeStage sets it up (cosmomodels.py:1680-1790)
+# --------------------------------------------------------------------------------------
+DEFAULT_RAMP = {"a": 15.0, "b": 0.3, "c": 1, "d": 2, "e": 1}          # cosmomodels.py:875-880
+
+
+def synthetic_source(t, k):
+    """A smooth, deterministic stand-in for the second-order source term S(t, k) (the reference
+    computes it with its `sourceterm` package, out of scope here): (T,) x (nk,) -> (T, nk) complex.
+    Used by tests/golden/make_golden.py (fed to the unmodified reference) and by the tests."""
+    t = np.asarray(t, dtype=float)[:, None]
+    k = np.asarray(k, dtype=float)[None, :]
+    amp = (k / 1e-60) ** -1.5 * np.exp(-0.08 * t)
+    return amp * (np.cos(0.9 * t + 3.0 * (k / 1e-58)) + 1j * np.sin(1.3 * t + 0.5))
+
+
+def so_start_indices(fotstartindex, fotstep):
+    """cosmomodels.py:1706-1709: first-order start rows on the second-order (2x) time grid."""
+    sotstep = fotstep * 2
+    return np.around(np.asarray(fotstartindex) * (fotstep / sotstep) + sotstep / 2).astype(int), sotstep
+
+
+def make_so_rhs(potential, params, k, ainit, fo_yresult, fo_simtstart, fo_tstep, bgepsilon, source,
+                ramp=None, tstart=None, tstartindex=None, so_tstep=None):
+    """Right-hand side of the real 4-vector (Re dphi2, Re dphi2', Im dphi2, Im dphi2') per mode.
+    ``fo_yresult`` (T_fo, 5, nk) complex is the single-field first-order trajectory, ``source``
+    (T_fo, nk) complex the source term (None: homogeneous equation), both sampled on the
+    first-order time grid; ``ramp`` (dict a, b, c, d, e) switches on the tanh ramp of
+    CanonicalRampedSecondOrder, which needs the per-mode first-order start times ``tstart``
+    (e-folds), the second-order start rows ``tstartindex`` and step ``so_tstep``."""
+    pot = globals()[potential] if isinstance(potential, str) else potential
+    k = np.asarray(k, dtype=float)
+
+    def rhs(y, t):
+        fotix = int(np.around((t - fo_simtstart) / fo_tstep))    # :724 / :911
+        fovars = fo_yresult[fotix]
+        phidot, H = fovars[1], fovars[2]                          # :741 (phi is only used by the potential)
+        eps = bgepsilon[fotix]
+        d2U = np.asarray(pot(fovars, params)[2]).reshape(-1)[0]   # column 0 of the first-order row
+        a = ainit * np.exp(t)
+        if source is None:
+            src = np.zeros(len(k), dtype=complex)
+        else:
+            src = np.array(source[fotix], dtype=complex)
+            if ramp is not None:                                  # :925-944
+                arg = t - tstart - ramp["b"]
+                need = np.abs(arg) < ramp["e"]
+                if np.any(need):
+                    r = (np.tanh(ramp["a"] * arg) + ramp["c"]) / ramp["d"]
+                    r[tstartindex == t / so_tstep] = 0
+                    src[need] = r[need] * src[need]
+        out = np.zeros((4, len(k)))
+        with np.errstate(all="ignore"):
+            damp, kah2 = 3 - eps, (k / (a * H)) ** 2
+            mass = d2U / H ** 2 - 3 * (phidot ** 2)
+            out[0] = y[1]
+            out[1] = np.real(-damp * y[1] - kah2 * y[0] - mass * y[0] - src.real)   # :754-755
+            out[2] = y[3]
+            out[3] = np.real(-damp * y[3] - kah2 * y[2] - mass * y[2] - src.imag)   # :761-762
+        return out
+    return rhs
+
+
+def second_order_run(potential, params, k, ainit, fo_tresult, fo_yresult, fotstart, fotstartindex,
+                     bgepsilon, source, fo_tstep=0.01, fo_simtstart=0.0, ramp=None, ystart=None,
+                     tstartindex=None):
+    """SOCanonicalThreeStage(...).run() (cosmomodels.py:1680-1790): returns (tresult, yresult
+    (T_so, 4, nk) float64, tstartindex)."""
+    k = np.asarray(k, dtype=float)
+    if tstartindex is None:
+        tstartindex, sotstep = so_start_indices(fotstartindex, fo_tstep)
+    else:
+        sotstep = fo_tstep * 2
+    if ystart is None:
+        ystart = np.zeros((4, len(k)))
+    simtstart, tend = fo_tresult[0], fo_tresult[-1]
+    f = make_so_rhs(potential, params, k, ainit, fo_yresult, fo_simtstart, fo_tstep, bgepsilon, source,
+                    ramp=ramp, tstart=np.asarray(fotstart, dtype=float), tstartindex=tstartindex,
+                    so_tstep=sotstep)
+    t, y = rk4_drive(np.asarray(ystart, dtype=float), simtstart, tstartindex, tend, sotstep, f)
+    return t, y, tstartindex

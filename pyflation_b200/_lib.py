@@ -17,6 +17,7 @@ PF_FLAG_BG_MISMATCH = 1
 PF_FLAG_TIMEOUT = 2
 PF_LAYOUT_FULL, PF_LAYOUT_PERT = 0, 1
 PF_PEER_HANDLE_BYTES = 64
+PF_SO_COEF = 6                # doubles per stage in pf_so_run's coefficient table
 
 # names every build must export (checked by tests/test_abi.py against the header)
 EXPORTS = [
@@ -26,6 +27,7 @@ EXPORTS = [
     "pf_rec_doubles", "pf_rec_bg_offset", "pf_bg_run", "pf_stage_table", "pf_fo_run", "pf_solve_scratch_doubles",
     "pf_fo_solve", "pf_pr_spectrum", "pf_pr_spectrum_pert", "pf_scatter_slab", "pf_copy_rows_d2h", "pf_copy_window_d2h",
     "pf_host_fill_background", "pf_crossing_rows", "pf_bunch_davies", "pf_derivs",
+    "pf_so_run", "pf_so_derivs",
     "pf_fp64_peak_probe", "pf_peer_alloc", "pf_peer_free", "pf_peer_export", "pf_peer_open", "pf_peer_close",
 ]
 
@@ -105,6 +107,10 @@ def lib():
     L.pf_bunch_davies.argtypes = [c_int, c_i64, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_dbl, c_dbl, c_int,
                                   c_int, c_vp, c_vp]
     L.pf_derivs.argtypes = [mp, c_int, c_i64, c_vp, c_dbl, c_vp, c_vp, c_vp]
+    L.pf_so_run.argtypes = [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp,
+                            ctypes.POINTER(c_dbl), c_i64, c_dbl, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp]
+    L.pf_so_derivs.argtypes = [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(c_dbl),
+                               c_vp, c_vp]
     L.pf_fp64_peak_probe.argtypes = [c_int, c_vp, c_i64, ctypes.POINTER(c_dbl)]
     L.pf_peer_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(c_vp)]
     L.pf_peer_free.argtypes = [c_vp]

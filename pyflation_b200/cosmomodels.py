@@ -6,7 +6,11 @@ slices ``H_ix, bg_ix, phis_ix, phidots_ix, pert_ix, dps_ix, dpdots_ix``) follow 
 (cosmomodels.py:53-206, 481-675, 973-1550, 2017-2197).  The integration itself is not done
 here: ``run()`` hands the model to :mod:`pyflation_b200.rk4`, which launches the CUDA kernels.
 
-Out of scope: second-order models, the HDF5 results files.
+Second-order stage (cosmomodels.py:678-971, 1680-1946): ``CanonicalSecondOrder``,
+``CanonicalRampedSecondOrder``, ``CanonicalHomogeneousSecondOrder`` and the drivers
+``SOCanonicalThreeStage`` / ``SOHorizonStart`` integrate on the GPU as well (pf_so_run) from a
+first-order model that carries a ``source`` array; computing that source term (the reference's
+``sourceterm`` package) is out of scope, as are the HDF5 results files.
 """
 import datetime
 import logging
@@ -249,6 +253,90 @@ class CanonicalFirstOrder(PhiModels):
             k = self.k
         pm = engine.make_model(self.potential_func, self.pot_params, self.nfields, self.ainit)
         return engine.derivs_device(pm, y, t, k)
+
+
+class _SecondOrderModel(PhiModels):
+    """What the three second-order classes share: y = (Re d2, Re d2', Im d2, Im d2') per mode,
+    integrated in e-folds from the rows of a first-order model (``second_stage``) and a source
+    term sampled on its time grid (``source``); both are attached by the driver
+    (cosmomodels.py:1755-1775)."""
+    ramped = False
+    with_source = True
+
+    def __init__(self, k=None, ainit=None, *args, **kwargs):
+        super(_SecondOrderModel, self).__init__(*args, **kwargs)
+        self.ainit = 1 if ainit is None else ainit
+        self.k = 10 ** (np.arange(10.0) - 8) if k is None else k
+        if self.ystart is None:
+            self.ystart = np.array([0.0, 0.0, 0.0, 0.0])
+
+    def _first_order_inputs(self):
+        fo = self.second_stage
+        y = fo.yresult
+        if y is None or y.shape[0] != len(fo.tresult) or y.shape[1] != 5:
+            raise ModelError("Second order models need the full single field first order trajectory.")
+        if not hasattr(fo, "bgepsilon"):
+            fo.bgepsilon = fo.bgmodel.getepsilon()
+        return dict(fo_bg0=np.real(y[:, 0:3, 0]), bgepsilon=fo.bgepsilon,
+                    fo_simtstart=fo.simtstart, fo_tstep=fo.tstep_wanted,
+                    fo_tsix=getattr(fo, "fotstartindex", None))
+
+    def derivs(self, y, t, **kwargs):
+        """Equation of motion for second order perturbations (cosmomodels.py:708-766, 797-848,
+        893-971), evaluated on the GPU (pf_so_derivs).  The solver never calls this method: it
+        recognises it and runs the second-order kernel."""
+        from . import engine
+        if kwargs.get("k") is None:
+            k, kix = self.k, np.arange(len(np.atleast_1d(self.k)))
+        else:
+            k, kix = kwargs["k"], kwargs.get("kix")
+        if kix is None:
+            raise ModelError("Need to specify kix in order to calculate 2nd order perturbation!")
+        kix = np.atleast_1d(kix)
+        fotix = None
+        if not self.with_source:
+            if kwargs.get("tix") is None:
+                raise ModelError("Need to specify tix in order to calculate 2nd order perturbation!")
+            fotix = int(kwargs["tix"])
+        inp = self._first_order_inputs()
+        if inp["fo_tsix"] is not None:
+            inp["fo_tsix"] = np.asarray(inp["fo_tsix"])[kix]
+        row = None
+        if self.with_source:
+            row = int(np.around((t - inp["fo_simtstart"]) / inp["fo_tstep"]))
+            row = np.asarray(self.source[row])[kix]
+        pm = engine.make_model(self.potential_func, self.pot_params, self.nfields, self.ainit)
+        extra = {}
+        if self.ramped:
+            extra = dict(ramp=self.rampargs, tstart=np.broadcast_to(self.tstart, np.shape(self.k))[kix],
+                         tsix=np.asarray(self.tstartindex)[kix])
+        return engine.so_derivs_device(pm, y, t, np.atleast_1d(k), so_tstep=self.tstep_wanted,
+                                       source_row=row, fotix=fotix, **dict(inp, **extra))
+
+
+class CanonicalSecondOrder(_SecondOrderModel):
+    """Second order model using efold as time variable (cosmomodels.py:678-766)."""
+
+
+class CanonicalHomogeneousSecondOrder(_SecondOrderModel):
+    """Second order homogeneous model: no source term; ``derivs`` needs the first-order row as
+    the keyword ``tix`` (cosmomodels.py:768-848), which no solver of the reference passes, so it
+    offers single right-hand-side evaluations only."""
+    with_source = False
+
+
+class CanonicalRampedSecondOrder(_SecondOrderModel):
+    """Second order model whose source term is switched on with a tanh ramp around each mode's
+    start time (cosmomodels.py:850-971):
+    ramp = (tanh(a*(t - t_ic - b)) + c)/d  while  abs(t - t_ic - b) < e."""
+    ramped = True
+
+    def __init__(self, k=None, ainit=None, *args, **kwargs):
+        super(CanonicalRampedSecondOrder, self).__init__(k, ainit, *args, **kwargs)
+        if "rampargs" not in kwargs:
+            self.rampargs = {"a": 15.0, "b": 0.3, "c": 1, "d": 2, "e": 1}
+        else:
+            self.rampargs = kwargs["rampargs"]
 
 
 class MultiStageDriver(CosmologicalModel):
@@ -579,6 +667,144 @@ class FOSuppressOneField(FOCanonicalTwoStage):
                             -arootk * osc * (1 + (self.k / (astar * Hstar)) * 1j),
                             skip=self.suppress_ix)
         return foystart
+
+
+class SOCanonicalThreeStage(MultiStageDriver):
+    """Runs third stage calculation (typically second order perturbations) using a two stage
+    model instance which carries a ``source`` array (cosmomodels.py:1680-1883)."""
+
+    def __init__(self, second_stage, soclass=None, ystart=None, **soclassargs):
+        self._adopt(second_stage)
+        self.nfields = second_stage.nfields
+        if ystart is None:
+            ystart = np.zeros((4, len(self.k)))
+        super(SOCanonicalThreeStage, self).__init__(**self._driver_kwargs(
+            ystart, self.fotstartindex, "rkdriver_tsix", soclassargs, nfields=self.nfields))
+        self._finish_init(soclass)
+
+    def _adopt(self, second_stage):
+        if not isinstance(second_stage, FOCanonicalTwoStage):
+            raise ModelError("Need to provide a FOCanonicalTwoStage instance to get first order results from!")
+        self.second_stage = second_stage
+        self.k = np.copy(second_stage.k)
+        self.simtstart = second_stage.tresult[0]
+        self.fotstart = np.copy(second_stage.fotstart)
+        self.fotstartindex = np.copy(second_stage.fotstartindex)
+        self.ainit = second_stage.ainit
+        self.potentials = second_stage.potentials
+        self.potential_func = second_stage.potential_func
+        self.pot_params = second_stage.pot_params
+
+    def _driver_kwargs(self, ystart, start_rows, solver, soclassargs, **more):
+        # start rows on the second-order time grid, whose step is twice the first-order one
+        fotstep = self.second_stage.tstep_wanted
+        sotstep = fotstep * 2
+        sotstartindex = np.around(start_rows * (fotstep / sotstep) + sotstep / 2).astype(int)
+        kwargs = dict(ystart=ystart, tstart=self.second_stage.tresult[0], tstartindex=sotstartindex,
+                      simtstart=self.simtstart, tend=self.second_stage.tresult[-1],
+                      tstep_wanted=sotstep, solver=solver,
+                      potential_func=self.second_stage.potential_func,
+                      pot_params=self.second_stage.pot_params, **more)
+        if soclassargs is not None:
+            kwargs.update(soclassargs)
+        return kwargs
+
+    def _finish_init(self, soclass):
+        self.soclass = CanonicalSecondOrder if soclass is None else soclass
+        self.somodel = None
+        source = getattr(self.second_stage, "source", None)
+        if source is None:
+            raise ModelError("First order model does not have a source term!")
+        self.source = source
+        self.setfieldindices()
+
+    def setfieldindices(self):
+        nf = self.nfields
+        # indices into self.second_stage.yresult
+        self.H_ix = nf * 2
+        self.bg_ix = slice(0, nf * 2 + 1)
+        self.phis_ix = slice(0, nf * 2, 2)
+        self.phidots_ix = slice(1, nf * 2, 2)
+        self.pert_ix = slice(nf * 2 + 1, None)
+        self.dps_ix = slice(nf * 2 + 1, None, 2)
+        self.dpdots_ix = slice(nf * 2 + 2, None, 2)
+        # indices of second order quantities, into self.yresult
+        self.dp2s_ix = slice(0, None, 2)
+        self.dp2dots_ix = slice(1, None, 2)
+
+    def setup_soclass(self):
+        """Initialize the second order class that will be used to run simulation."""
+        self.somodel = self.soclass(ystart=self.ystart, tstart=self.fotstart,
+                                    tstartindex=self.tstartindex, simtstart=self.simtstart,
+                                    tend=self.tend, tstep_wanted=self.tstep_wanted,
+                                    solver=self.solver, k=self.k, ainit=self.ainit,
+                                    potential_func=self.potential_func, pot_params=self.pot_params,
+                                    cq=self.cq, nfields=self.nfields)
+        self.somodel.source = self.source
+        self.somodel.second_stage = self.second_stage
+
+    def runso(self):
+        """Run second order model."""
+        self.setup_soclass()
+        self._log.info("Beginning second order run...")
+        try:
+            self.somodel.run(saveresults=False)
+        except ModelError:
+            self._log.exception("Error in second order run, aborting!")
+            raise
+        self.tresult, self.yresult = self.somodel.tresult, self.somodel.yresult
+
+    def run(self, saveresults=True):
+        """Run simulation and save results."""
+        self.runso()
+        self.lastparams = self.callingparams()
+        if saveresults:
+            try:
+                self._log.info("Results saved in " + self.saveallresults())
+            except IOError:
+                self._log.exception("Error trying to save results! Results NOT saved.")
+
+    @property
+    def deltaphi(self):
+        """delta phi = dp1 + dp2/2 for all timesteps and k modes.  The reference's expression
+        (cosmomodels.py:1843-1846) reads rows 3 and 5 of the first-order result, i.e. the layout
+        of real/imaginary rows it had before the mode functions became complex; with the complex
+        layout the first-order mode is row ``dps_ix`` itself, sampled on the second-order grid."""
+        if not hasattr(self, "_deltaphi"):
+            ratio = int(np.around(self.tstep_wanted / self.second_stage.tstep_wanted))
+            dp1 = self.second_stage.yresult[::ratio, self.dps_ix][:self.yresult.shape[0], 0]
+            dp2 = self.yresult[:, 0, :] + self.yresult[:, 2, :] * 1j
+            self._deltaphi = dp1 + 0.5 * dp2
+        return self._deltaphi
+
+    # results of the stage below
+    phis = property(lambda self: self.second_stage.yresult[:, self.phis_ix])
+    phidots = property(lambda self: self.second_stage.yresult[:, self.phidots_ix])
+    H = property(lambda self: self.second_stage.yresult[:, self.H_ix])
+    dpmodes = property(lambda self: self.second_stage.yresult[:, self.dps_ix])
+    dpdotmodes = property(lambda self: self.second_stage.yresult[:, self.dpdots_ix])
+    # second order quantities
+    dp2modes = property(lambda self: self.yresult[:, self.dp2s_ix])
+    dp2dotmodes = property(lambda self: self.yresult[:, self.dp2dots_ix])
+    a = property(lambda self: self.ainit * np.exp(self.tresult))
+
+
+class SOHorizonStart(SOCanonicalThreeStage):
+    """Second order calculation that starts at horizon crossing (k = aH) instead of the first
+    order start (cosmomodels.py:1885-1946).  The reference asks for the solver "rkdriver_new",
+    which its rk4 module does not have (ValueError "Solver not recognized!", as here); pass
+    ``solver="rkdriver_tsix"`` to run it."""
+
+    def __init__(self, second_stage, soclass=None, ystart=None, **soclassargs):
+        self._adopt(second_stage)
+        self.nfields = second_stage.nfields
+        if ystart is None:
+            ystart = np.zeros((4, len(self.k)))
+        rows = second_stage._crossing_rows(second_stage.k, second_stage.bgmodel.tresult,
+                                           second_stage.bgmodel.yresult[:, 2], factor=1)
+        super(SOCanonicalThreeStage, self).__init__(**self._driver_kwargs(
+            ystart, np.asarray(rows), "rkdriver_new", soclassargs))
+        self._finish_init(soclass)
 
 
 def make_wrapper_model(modelfile, *args, **kwargs):

@@ -9,7 +9,7 @@ namespace pf {
 template <int NF>
 struct FoShape {
     static constexpr int NB = 2 * NF + 1;
-    static constexpr int SW = 2 + NF * NF;          // doubles per stage: A, R, C[NF][NF]
+    static constexpr int SW = rec_stage_width(NF);  // doubles per stage: A, R, C[NF][NF] (NF > 8: factored slot)
     static constexpr int REC = rec_of(NF);
     static constexpr int BG_OFF = 4 * SW;           // background row sits after the 4 stages
     static constexpr int CH_RAW = 16384 / (REC * 8);

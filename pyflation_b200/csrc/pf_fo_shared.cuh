@@ -122,6 +122,7 @@ int rt_bg_run(const pf_model* m, int64_t T, double h, int64_t n0, const double* 
 int rt_stage_table(const pf_model* m, int64_t T, double simtstart, double h, int64_t n0,
                    const double* stagey, double* rec, cudaStream_t st);
 int rt_fo_run(const pf_model* m, const FoArgs& a, cudaStream_t st);
+bool wide_fo_run(int nf, const FoArgs& a, cudaStream_t st);   // pf_fo_wide.cu: nf = 9..16
 int rt_potential_eval(const pf_model* m, int64_t n, const double* y, double* U, double* dU, double* d2U,
                       cudaStream_t st);
 int rt_derivs(const pf_model* m, int first_order, int64_t ncol, const double* y, double t, const double* k,

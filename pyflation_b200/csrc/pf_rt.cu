@@ -153,6 +153,9 @@ struct StageRt {
 };
 
 // Mode kernel, runtime nf.  Row logic identical to fo_consume<NF, 1> (pf_fo_generic.cuh).
+// MAXF (16 / 32 / 64) sizes the per-thread local arrays; with the CTA size chosen by the launcher
+// (128 / 64 / 32 threads) a CTA's 6 * MAXF * 8 bytes per thread stay at 96 KB, i.e. inside L1.
+template <int MAXF>
 __global__ void __launch_bounds__(128) fo_rt_kernel(FoArgs a, int nf) {
     const int NB = 2 * nf + 1, SW = rec_stage_width(nf), REC = rec_of(nf), BG_OFF = 4 * SW;
     const bool pert = a.layout == PF_LAYOUT_PERT;
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(128) fo_rt_kernel(FoArgs a, int nf) {
     const double h = a.h, hh = h * 0.5, h6 = h / 6.0;     // rk4.py:31-32
     const double nan = qnan();
 
-    double x[RT], v[RT], ax[RT], av[RT], xt[RT], vt[RT];
+    double x[MAXF], v[MAXF], ax[MAXF], av[MAXF], xt[MAXF], vt[MAXF];
     for (int i = 0; i < nf; ++i) { x[i] = 0.0; v[i] = 0.0; }
     if (a.t0 > ts) {                                      // resume a windowed run
         for (int i = 0; i < nf; ++i) {
@@ -375,9 +378,26 @@ int rt_stage_table(const pf_model* m, int64_t T, double simtstart, double h, int
 }
 
 int rt_fo_run(const pf_model* m, const FoArgs& a, cudaStream_t st) {
-    const int block = 128;
-    dim3 grid((unsigned)((a.nk + block / 2 - 1) / (block / 2)), (unsigned)m->nfields, 1);
-    fo_rt_kernel<<<grid, block, 0, st>>>(a, m->nfields);
+    const int nf = m->nfields;
+    // 9..16 fields: register-resident factored instantiations (pf_fo_wide.cu); PF_FO_RT forces the
+    // local-memory kernel below (A/B measurements, and the path every nf > 16 takes)
+    const bool rt_only = getenv("PF_FO_RT") != nullptr;   // read per call: the tests flip it
+    if (!rt_only && wide_fo_run(nf, a, st)) {
+        PF_CUDA_CHECK(cudaGetLastError(), "pf_fo_run launch (wide nf)");
+        return PF_OK;
+    }
+    const int block = nf <= 16 ? 128 : (nf <= 32 ? 64 : 32);
+    dim3 grid((unsigned)((a.nk + block / 2 - 1) / (block / 2)), (unsigned)nf, 1);
+    static bool carved = false;
+    if (!carved) {                                        // no shared memory used: all of it to L1
+        cudaFuncSetAttribute(fo_rt_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+        cudaFuncSetAttribute(fo_rt_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+        cudaFuncSetAttribute(fo_rt_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+        carved = true;
+    }
+    if (nf <= 16) fo_rt_kernel<16><<<grid, block, 0, st>>>(a, nf);
+    else if (nf <= 32) fo_rt_kernel<32><<<grid, block, 0, st>>>(a, nf);
+    else fo_rt_kernel<64><<<grid, block, 0, st>>>(a, nf);
     PF_CUDA_CHECK(cudaGetLastError(), "pf_fo_run launch (runtime nf)");
     return PF_OK;
 }

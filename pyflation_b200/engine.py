@@ -600,3 +600,153 @@ def derivs_device(model, y, t, k=None):
     if not np.iscomplexobj(ynp):
         res = np.ascontiguousarray(res.real)
     return res[:, 0] if single else res
+
+
+# ---- second-order stage (K9) ------------------------------------------------------------------
+def so_stage_coefficients(model, t, fo_bg0, bgepsilon, fo_simtstart, fo_tstep, so_tstep, device=None):
+    """The time-only factors of the second-order right-hand side at the times ``t`` (any shape):
+    array t.shape + (PF_SO_COEF,) of  3 - eps,  1/(aH)^2,  V''/H^2 - 3 phi'^2,  t,  fotix,  t/h
+    (cosmomodels.py:724-755), with eps, phi', H, V'' read at row fotix of the first-order result
+    (``fo_bg0`` [T_fo, 3]: column 0's phi, phi', H) / of ``bgepsilon``.  V'' is evaluated on the
+    device (K0) for every first-order row once."""
+    dev = require_cuda(device)
+    t = np.asarray(t, dtype=np.float64)
+    fo_bg0 = np.ascontiguousarray(np.real(fo_bg0), dtype=np.float64)
+    T_fo = fo_bg0.shape[0]
+    fotix = np.around((t - fo_simtstart) / fo_tstep).astype(np.int64)          # :724
+    if fotix.size and (fotix.min() < 0 or fotix.max() >= min(T_fo, len(bgepsilon))):
+        raise IndexError("second-order stage time outside the first-order result: row %d of %d"
+                         % (int(fotix.max() if fotix.max() >= T_fo else fotix.min()), T_fo))
+    with torch.cuda.device(dev):
+        d2U = potential_eval_device(model, torch.as_tensor(fo_bg0).to(dev))[2][:, 0, 0].cpu().numpy()
+    with np.errstate(all="ignore"):
+        phidot, H = fo_bg0[fotix, 1], fo_bg0[fotix, 2]
+        a = model.ainit * np.exp(t)                                             # :748
+        coef = np.empty(t.shape + (_lib.PF_SO_COEF,), dtype=np.float64)
+        coef[..., 0] = 3 - np.asarray(bgepsilon, dtype=np.float64)[fotix]
+        coef[..., 1] = 1.0 / (a * H) ** 2
+        coef[..., 2] = d2U[fotix] / H ** 2 - 3 * (phidot ** 2)
+        coef[..., 3] = t
+        coef[..., 4] = fotix
+        coef[..., 5] = t / so_tstep                                             # :935
+    return coef
+
+
+def _ramp_array(ramp):
+    if ramp is None:
+        return None, None
+    arr = (ctypes.c_double * 5)(*[float(ramp[q]) for q in ("a", "b", "c", "d", "e")])
+    return arr, ctypes.cast(arr, ctypes.POINTER(ctypes.c_double))
+
+
+class SecondOrderProblem(object):
+    """Device-resident inputs of one second-order solve (what SOCanonicalThreeStage.runso hands to
+    rkdriver_tsix, cosmomodels.py:1755-1790)."""
+
+    def __init__(self, model, k, tsix, ystart, simtstart, T, h, fo_bg0, bgepsilon, fo_simtstart,
+                 fo_tstep, fo_tsix=None, source=None, ramp=None, tstart=None, device=None):
+        self.dev = require_cuda(device)
+        self.model, self.T, self.h, self.simtstart = model, int(T), float(h), float(simtstart)
+        k = np.ascontiguousarray(np.atleast_1d(k), dtype=np.float64)
+        self.nk = nk = k.shape[0]
+        tsix = np.ascontiguousarray(np.atleast_1d(tsix), dtype=np.int64)
+        ystart = np.ascontiguousarray(ystart, dtype=np.float64)
+        if ystart.shape != (4, nk) or tsix.shape[0] != nk:
+            raise ValueError("ystart must have shape (4, len(k))")
+        # three stage times per step n -> n+1                       rk4.py:27-55, 116-118
+        x = self.simtstart + np.arange(self.T) * self.h
+        t = np.stack([x, x + self.h * 0.5, x + self.h], axis=1)
+        t[self.T - 1] = t[max(self.T - 2, 0)]                       # the last row takes no step
+        coef = so_stage_coefficients(model, t, fo_bg0, bgepsilon, fo_simtstart, fo_tstep, self.h, self.dev)
+        self.h2d_bytes = 0
+        with torch.cuda.device(self.dev):
+            up = lambda a: torch.as_tensor(a).to(self.dev)
+            self.k, self.tsix, self.ystart, self.coef = up(k), up(tsix), up(ystart), up(coef)
+            self.fo_tsix = None if fo_tsix is None else up(np.ascontiguousarray(fo_tsix, dtype=np.int64))
+            self.tstart = None
+            if ramp is not None:
+                if tstart is None:
+                    raise ValueError("a ramped source needs the first-order start times")
+                self.tstart = up(np.ascontiguousarray(np.broadcast_to(np.asarray(tstart, dtype=np.float64), (nk,))))
+            self.source = None
+            if source is not None:
+                if torch.is_tensor(source):
+                    src = source.to(self.dev)
+                else:
+                    src = np.asarray(source)
+                    self.h2d_bytes += src.shape[0] * nk * 16
+                    src = up(np.ascontiguousarray(src, dtype=np.complex128))
+                if src.dtype != torch.complex128 or src.dim() != 2 or src.shape[1] != nk:
+                    raise ValueError("source must be complex128 of shape (T_fo, len(k))")
+                if int(coef[: max(self.T - 1, 1), :, 4].max()) >= src.shape[0]:
+                    raise IndexError("second-order stage time outside the source term")
+                self.source = src.contiguous()
+            self.state = torch.zeros((4, nk), dtype=torch.float64, device=self.dev)
+        self._ramp_keep, self._ramp_ptr = _ramp_array(ramp)
+
+    def launch(self, t0, t1, yout, out_every=1, stream=None, out_pitch=0):
+        L = _lib.lib()
+        src = self.source
+        with torch.cuda.device(self.dev):
+            _lib.check(L.pf_so_run(self.nk, _ptr(self.k), _ptr(self.tsix), _ptr(self.fo_tsix),
+                                   _ptr(self.ystart), _ptr(self.coef), _ptr(src),
+                                   0 if src is None else src.shape[0], 0 if src is None else src.shape[1],
+                                   _ptr(self.tstart), self._ramp_ptr, self.T, self.h, int(t0), int(t1),
+                                   _ptr(self.state), _ptr(yout), int(out_every), int(out_pitch),
+                                   _stream_ptr(stream)))
+
+
+def second_order_device(prob, out=None, out_every=1):
+    """One launch over [0, T): rows 0, out_every, ... as a (rows, 4, nk) float64 CUDA tensor."""
+    rows = (prob.T + out_every - 1) // out_every
+    if out is None:
+        out = torch.empty((rows, 4, prob.nk), dtype=torch.float64, device=prob.dev)
+    prob.launch(0, prob.T, out, out_every)
+    return out
+
+
+def second_order_host(prob, slab_bytes=4 << 30):
+    """The whole (T, 4, nk) float64 trajectory in host memory; results larger than ``slab_bytes``
+    go through time windows (state carried on the device between them)."""
+    T, nk = prob.T, prob.nk
+    out = np.empty((T, 4, nk), dtype=np.float64)
+    rows = max(1, min(T, slab_bytes // (32 * nk)))
+    with torch.cuda.device(prob.dev):
+        slab = torch.empty((rows, 4, nk), dtype=torch.float64, device=prob.dev)
+        for t0 in range(0, T, rows):
+            t1 = min(T, t0 + rows)
+            prob.launch(t0, t1, slab, 1)
+            out[t0:t1] = slab[: t1 - t0].cpu().numpy()
+    prob.d2h_bytes = out.nbytes
+    return out
+
+
+def so_derivs_device(model, y, t, k, fo_bg0, bgepsilon, fo_simtstart, fo_tstep, so_tstep, source_row=None,
+                     fo_tsix=None, ramp=None, tstart=None, tsix=None, fotix=None):
+    """One second-order right-hand side on the device (pf_so_derivs): dydx (4, nk) for y (4, nk).
+    ``fotix`` overrides the first-order row (CanonicalHomogeneousSecondOrder passes ``tix``)."""
+    L = _lib.lib()
+    dev = require_cuda()
+    k = np.ascontiguousarray(np.atleast_1d(k), dtype=np.float64)
+    nk = k.shape[0]
+    y = np.ascontiguousarray(np.broadcast_to(np.asarray(y, dtype=np.float64).reshape(4, -1), (4, nk)))
+    if fotix is None:
+        coef = so_stage_coefficients(model, np.array([t]), fo_bg0, bgepsilon, fo_simtstart, fo_tstep, so_tstep, dev)[0]
+    else:
+        tt = fo_simtstart + fotix * fo_tstep
+        coef = so_stage_coefficients(model, np.array([tt]), fo_bg0, bgepsilon, fo_simtstart, fo_tstep, so_tstep, dev)[0]
+        a = model.ainit * np.exp(t)
+        coef[1] = 1.0 / (a * np.real(fo_bg0[fotix, 2])) ** 2
+        coef[3], coef[5] = t, t / so_tstep
+    keep, rptr = _ramp_array(ramp)
+    with torch.cuda.device(dev):
+        up = lambda a: None if a is None else torch.as_tensor(np.ascontiguousarray(a)).to(dev)
+        kd, yd, cd = up(k), up(y), up(coef)
+        sd = up(None if source_row is None else np.asarray(source_row, dtype=np.complex128))
+        td = up(None if tstart is None else np.broadcast_to(np.asarray(tstart, dtype=np.float64), (nk,)))
+        xd = up(None if tsix is None else np.asarray(tsix, dtype=np.int64))
+        fd = up(None if fo_tsix is None else np.asarray(fo_tsix, dtype=np.int64))
+        out = torch.empty_like(yd)
+        _lib.check(L.pf_so_derivs(nk, _ptr(kd), _ptr(xd), _ptr(fd), _ptr(yd), _ptr(cd), _ptr(sd), _ptr(td),
+                                  rptr, _ptr(out), _stream_ptr()))
+        return out.cpu().numpy()

@@ -4,7 +4,8 @@ Same names and call signatures as the reference: :func:`rkdriver_tsix`, :func:`r
 :class:`SimRunError`.  A Python callable cannot cross the C ABI, so instead of calling
 ``derivs`` the driver looks at the model it is bound to (``derivs.__self__``): a
 ``CanonicalBackground`` goes to the background kernel, a ``CanonicalFirstOrder`` to the fused
-first-order kernel.  Any other right-hand side raises ``NotImplementedError``: there is no
+first-order kernel, a ``CanonicalSecondOrder`` / ``CanonicalRampedSecondOrder`` to the
+second-order kernel.  Any other right-hand side raises ``NotImplementedError``: there is no
 CPU fallback.
 """
 import logging
@@ -71,9 +72,12 @@ def _bound_model(derivs):
     if isinstance(owner, c.CanonicalBackground) and getattr(derivs, "__func__", None) is \
             c.CanonicalBackground.derivs:
         return "bg", owner
+    if isinstance(owner, (c.CanonicalSecondOrder, c.CanonicalRampedSecondOrder)) and \
+            getattr(derivs, "__func__", None) is c._SecondOrderModel.derivs:
+        return "so", owner
     raise NotImplementedError(
-        "pyflation_b200.rk4 integrates CanonicalBackground.derivs and CanonicalFirstOrder.derivs "
-        "on the GPU; an arbitrary Python `derivs` (%r) cannot be run and there is no CPU "
+        "pyflation_b200.rk4 integrates CanonicalBackground.derivs, CanonicalFirstOrder.derivs and "
+        "Canonical(Ramped)SecondOrder.derivs on the GPU; an arbitrary Python `derivs` (%r) cannot be run and there is no CPU "
         "fallback." % (derivs,))
 
 
@@ -121,6 +125,8 @@ def rkdriver_tsix(ystart, simtstart, tsix, tend, h, derivs, yresult_out=None, ro
     try:
         if kind == "bg":
             yarr = _run_background(model, ystart, simtstart, tsix, T, h)
+        elif kind == "so":
+            yarr = _run_second_order(model, ystart, simtstart, tsix, T, h)
         else:
             if row_stride == "last":
                 row_stride = max(1, T - 1)
@@ -193,6 +199,29 @@ def _run_first_order(model, ystart, simtstart, tsix, T, h, yresult_out=None, row
     yarr = yresult_out if (yresult_out is not None and not torch.is_tensor(yresult_out)) else res.numpy()
     if pr_dev is not None:
         _remember_pr(yarr, pr_dev)
+    return yarr
+
+
+def _run_second_order(model, ystart, simtstart, tsix, T, h):
+    """rkdriver_tsix for CanonicalSecondOrder / CanonicalRampedSecondOrder.derivs: the model
+    carries ``second_stage`` (first-order results) and ``source`` (cosmomodels.py:1773-1775)."""
+    k = np.atleast_1d(np.asarray(model.k, dtype=np.float64))
+    if ystart.shape != (4, k.shape[0]) or tsix.shape[0] != k.shape[0]:
+        raise SimRunError("ystart must have shape (4, len(k))")
+    if np.iscomplexobj(ystart):
+        raise NotImplementedError("second order runs are real valued")
+    inp = model._first_order_inputs()
+    fo_tsix = inp["fo_tsix"]
+    if fo_tsix is not None and int(np.asarray(fo_tsix)[0]) != int(np.min(fo_tsix)):
+        # the potential is evaluated on column 0 of the first-order row (cmpotentials.py, single
+        # field functions take y[:, 0]): as in the first-order run, column 0 must start first
+        raise SimRunError("column 0 must be the earliest-starting mode (k ascending)")
+    pm = engine.make_model(model.potential_func, model.pot_params, model.nfields, model.ainit)
+    ramp = model.rampargs if model.ramped else None
+    prob = engine.SecondOrderProblem(pm, k, tsix, ystart, simtstart, T, h, source=model.source,
+                                     ramp=ramp, tstart=model.tstart if model.ramped else None, **inp)
+    yarr = engine.second_order_host(prob)
+    last_transfer.update(h2d_bytes=prob.h2d_bytes, d2h_bytes=prob.d2h_bytes)
     return yarr
 
 

@@ -80,4 +80,6 @@ if __name__ == "__main__":
     elif which == "c1": main("msqphisq", 1, 2053, (18.0, -0.1, 0.0))
     elif which == "c3": main("hybridquadratic", 2, int(sys.argv[2]) if len(sys.argv) > 2 else 2**16, (12.0, 1/300.0, 12.0, 49/300.0, 0))
     elif which == "c5": main("msqphisq", 1, int(sys.argv[2]) if len(sys.argv) > 2 else 2**20, (18.0, -0.1, 0.0))
+    elif which.startswith("nf"):      # e.g. nf10 16384: nflation with that many fields (runtime-nfields kernels above 8)
+        nf = int(which[2:]); main("nflation", nf, int(sys.argv[2]) if len(sys.argv) > 2 else 2**13, None, {"nfields": nf})
     elif which == "c4": main("nflation", 8, int(sys.argv[2]) if len(sys.argv) > 2 else 2**13, None, {"nfields": 8})

@@ -76,6 +76,12 @@ FIXTURES = {
                   "FOCanonicalTwoStage", {}),
     "nflation10": ("nflation", 10, {"nfields": 10}, None, 2 ** 10, 2, 100,
                    "FOCanonicalTwoStage", {}),
+    # register-resident instantiations for 9..16 fields (pf_fo_wide.cu): an odd count, and the
+    # largest one (whose kernel spills a few registers)
+    "nflation13": ("nflation", 13, {"nfields": 13}, None, 2 ** 10, 2, 100,
+                   "FOCanonicalTwoStage", {}),
+    "nflation16": ("nflation", 16, {"nfields": 16}, None, 2 ** 10, 2, 100,
+                   "FOCanonicalTwoStage", {}),
     "hybridquartic": ("hybridquartic", 2, {"nfields": 2}, [1e-2, 2e-8, 1.63e-9, 3.26e-7, 0],
                       2 ** 10, 5, 50, "FOCanonicalTwoStage", {}),
     "productexponential": ("productexponential", 2, {"nfields": 2}, [18.0, 0.0, 0.001, 0, 0],
@@ -170,6 +176,85 @@ def make_fo(ref, name):
     np.savez_compressed(path, **out)
     print("%-26s nf=%d nk=%d T=%d rows=%d wall=%.1fs -> %.0f KB" % (
         name, nf, len(k), T, len(rows), wall, os.path.getsize(path) / 1024.0))
+
+
+# second-order stage: name -> (first-order fixture it starts from, #modes kept)
+SO_FIXTURES = {
+    "so_msqphisq": ("c1_msqphisq_k4", 4),
+    "so_lambdaphi4": ("c2_lambdaphi4_2p16", 4),       # d2U depends on phi
+}
+
+
+def make_so(ref, name):
+    """SOCanonicalThreeStage on top of a reference first-order run, with oracle.synthetic_source
+    as the source term, for CanonicalSecondOrder and CanonicalRampedSecondOrder; plus single
+    right-hand-side evaluations of the three second-order classes."""
+    import pyflation_oracle as oracle
+    fo_name, nkeep = SO_FIXTURES[name]
+    pot, nf, params, bgystart, grid, _, _, cls, extra = FIXTURES[fo_name]
+    kfull = k4_grid(ref) if grid == "K4" else np.linspace(KMIN, KMAX, grid)
+    kix = subsample(len(kfull), nkeep)
+    k = kfull[kix]
+    c = ref.cosmomodels
+    m = getattr(c, cls)(k=k, potential_func=pot, pot_params=dict(params), nfields=nf, cq=50,
+                        solver="rkdriver_tsix", bgystart=np.array(bgystart, dtype=float), **extra)
+    m.run(saveresults=False)
+    m.source = oracle.synthetic_source(m.tresult, k)
+    out = dict(potential=pot, nfields=nf, fo_fixture=fo_name,
+               param_keys=np.array(sorted(params.keys())),
+               param_vals=np.array([float(params[q]) for q in sorted(params.keys())]),
+               bgystart=np.array(m.bgystart, dtype=float), k=k, kix=kix,
+               ainit=np.asarray(m.ainit, dtype=float), fo_tstep=float(m.tstep_wanted),
+               fo_simtstart=float(m.simtstart), fo_tresult=m.tresult,
+               fo_bg0=np.real(m.yresult[:, 0:3, 0]), fotstart=m.fotstart,
+               fotstartindex=m.fotstartindex, bgepsilon=m.bgepsilon)
+    fo_y = m.yresult
+    for tag, soclass in (("plain", c.CanonicalSecondOrder), ("ramped", c.CanonicalRampedSecondOrder)):
+        t0 = time.time()
+        so = c.SOCanonicalThreeStage(m, soclass=soclass)
+        so.run(saveresults=False)
+        T = so.yresult.shape[0]
+        rows = keep_rows(T, so.tstartindex, 40)
+        out[tag + "_tstartindex"] = np.asarray(so.tstartindex)
+        out[tag + "_tresult"] = so.tresult
+        out[tag + "_rows"] = rows
+        out[tag + "_yrows"] = so.yresult[rows]
+        out[tag + "_wall_s"] = time.time() - t0
+        out["so_tstep"] = float(so.tstep_wanted)
+        out["so_simtstart"] = float(so.simtstart)
+        out["so_tend"] = float(so.tend)
+        # single right-hand sides: a running row, a half step, and rows inside the ramp window
+        sm = so.somodel
+        probe_rows = sorted(set([int(so.tstartindex.max()) + 200, int(so.tstartindex.min()) + 3,
+                                 int(so.tstartindex.min()), int(so.tstartindex.max()) + 20]))
+        ts, ys, ds = [], [], []
+        for r in probe_rows:
+            for half in (0.0, 0.5):
+                t = so.simtstart + (r + half) * so.tstep_wanted
+                y = np.nan_to_num(so.yresult[r]) + 1e-3 * np.arange(1, 5)[:, None]
+                ts.append(t); ys.append(y); ds.append(sm.derivs(y, t))
+        out[tag + "_derivs_t"] = np.array(ts)
+        out[tag + "_derivs_y"] = np.array(ys)
+        out[tag + "_derivs_dydx"] = np.array(ds)
+        m.yresult = fo_y                     # SOCanonicalThreeStage re-binds it (cosmomodels.py:1749)
+    out["rampargs_keys"] = np.array(sorted(so.somodel.rampargs.keys()))
+    out["rampargs_vals"] = np.array([float(so.somodel.rampargs[q]) for q in sorted(so.somodel.rampargs.keys())])
+    # homogeneous class: derivs only (it needs a tix keyword no solver of the reference passes)
+    hm = c.CanonicalHomogeneousSecondOrder(k=k, ainit=m.ainit, ystart=np.zeros((4, len(k))),
+                                           tstart=m.fotstart, tstartindex=so.tstartindex,
+                                           simtstart=so.simtstart, tend=so.tend,
+                                           tstep_wanted=so.tstep_wanted, solver="rkdriver_tsix",
+                                           potential_func=pot, pot_params=dict(params), nfields=nf)
+    hm.second_stage = m
+    tix = int(m.fotstartindex.max()) + 300
+    yh = 1e-3 * np.arange(1, 5)[:, None] * np.ones((1, len(k)))
+    out["homog_tix"] = tix
+    out["homog_t"] = float(m.tresult[tix])
+    out["homog_y"] = yh
+    out["homog_dydx"] = hm.derivs(yh, m.tresult[tix], tix=tix)
+    path = os.path.join(HERE, "%s.npz" % name)
+    np.savez_compressed(path, **out)
+    print("%-26s nk=%d T_so=%d rows=%d -> %.0f KB" % (name, len(k), T, len(rows), os.path.getsize(path) / 1024.0))
 
 
 def make_potentials(ref):
@@ -288,7 +373,7 @@ def make_pzeta(ref):
 
 def main(argv):
     ref = ref_shim.load()
-    names = argv[1:] or (["potentials", "kat"] + list(FIXTURES) + ["pzeta"])
+    names = argv[1:] or (["potentials", "kat"] + list(FIXTURES) + ["pzeta"] + list(SO_FIXTURES))
     for name in names:
         if name == "potentials":
             make_potentials(ref)
@@ -296,6 +381,8 @@ def main(argv):
             make_kat(ref)
         elif name == "pzeta":
             make_pzeta(ref)
+        elif name in SO_FIXTURES:
+            make_so(ref, name)
         else:
             make_fo(ref, name)
 

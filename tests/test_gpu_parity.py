@@ -140,6 +140,32 @@ def test_full_two_stage_run_matches_reference_golden(name):
     assert rel_err(m.Pr[rows], g["Pr_rows"]) < tol_bg
 
 
+def test_runtime_nfields_kernel_matches_golden_and_the_register_kernel(monkeypatch):
+    """nflation with 9..16 fields runs register-resident instantiations (pf_fo_wide.cu); above
+    that -- and here, forced by PF_FO_RT -- the runtime-nfields kernel with its state in local
+    memory.  Same records, same formulas: both must match the reference's nf = 10 golden rows."""
+    from pyflation_b200 import cosmomodels as c
+    g = load_fo("nflation10")
+    nf = g["nfields"]
+
+    def run():
+        fo = c.CanonicalFirstOrder(ystart=g["foystart"].copy(), tstart=g["fotstart"], simtstart=0.0,
+                                   tstartindex=g["fotstartindex"], tend=float(g["fotend"]),
+                                   tstep_wanted=float(g["h"]), solver="rkdriver_tsix", k=g["k"],
+                                   ainit=g["ainit"], potential_func=g["potential"],
+                                   pot_params=dict(g["params"]), nfields=nf)
+        fo.run(saveresults=False)
+        return fo.yresult
+    wide = run()
+    monkeypatch.setenv("PF_FO_RT", "1")
+    rt = run()
+    monkeypatch.delenv("PF_FO_RT")
+    for y in (wide, rt):
+        assert rel_err(y[g["rows"]][:, :2 * nf + 1], g["yrows"][:, :2 * nf + 1]) < TOL
+        assert mode_rel_err(y[g["rows"]], g["yrows"], nf) < TOL
+    assert mode_rel_err(wide, rt, nf) < 1e-11
+
+
 def _problem(g, m=None, k=None):
     """Device problem for golden fixture g (bg + ICs through the package)."""
     from pyflation_b200 import cosmomodels as c, engine
@@ -247,14 +273,18 @@ def test_unsorted_start_rows_through_the_compact_host_path():
 
 
 @pytest.mark.parametrize("name,nk", [("c2_lambdaphi4_2p16", 16411), ("c2_lambdaphi4_2p16", 333),
-                                     ("c3_hybridquadratic_2p20", 301), ("nflation5", 97), ("nflation10", 37)])
-def test_kernels_stay_inside_their_buffers(name, nk):
+                                     ("c3_hybridquadratic_2p20", 301), ("nflation5", 97), ("nflation10", 37), ("nflation13", 37),
+                                     ("rt:nflation10", 37)])
+def test_kernels_stay_inside_their_buffers(name, nk, monkeypatch):
     """compute-sanitizer is not available on the GPU pool, so the bounds check is our own: every
     buffer a mode kernel writes (trajectory, carried state, solve scratch) sits between guard
     bands of a sentinel, for full / strided / windowed / pitched launches (fused, plain, lock-step,
     factored and runtime-nfields kernels), and the guards must come back untouched."""
     import torch
     from pyflation_b200 import engine
+    if name.startswith("rt:"):                    # the local-memory kernel every nf > 16 runs
+        monkeypatch.setenv("PF_FO_RT", "1")
+        name = name[3:]
     g = load_fo(name)
     nf = g["nfields"]
     m, prob = _problem(g, k=np.linspace(KMIN, KMAX, nk))
