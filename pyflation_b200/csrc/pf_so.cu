@@ -11,17 +11,16 @@
 //     y0' = y1,   y1' = -( (3 - eps) y1 + (k/(aH))^2 y0 + (V''/H^2 - 3 phi'^2) y0 + S )
 // Everything except k and S is a function of the stage time alone, so the host tabulates it once
 // per run ("coefficients": three stage times per step, PF_SO_COEF doubles each) and the kernel
-// is what remains: one thread per (k, re|im), 16 B of source read and 16 B of result written per
-// thread and step -- HBM-bound.  Consecutive lanes hold (re, im) of consecutive k: a warp reads
-// one contiguous 256-byte piece of a source row and writes two 128-byte pieces of result rows.
-// The source values of the next PF_SO_AHEAD steps are loaded into registers before they are
+// is what remains: one thread per mode, 32 B of source read and 32 B of result written per mode
+// and step -- HBM-bound.  The source values of the next PF_SO_AHEAD steps are loaded into registers before they are
 // needed (they do not depend on the state), which is what keeps enough bytes in flight.
 #include "pf_common.cuh"
+#include "pf_fo_shared.cuh"
 
 namespace pf {
 
-constexpr int SO_BLOCK = 128;
-constexpr int SO_AHEAD = 4;          // steps of source values held in registers ahead of the RK4
+constexpr int SO_BLOCK = 64;
+constexpr int SO_AHEAD = 6;          // steps of source values held in registers ahead of the RK4
 constexpr int SO_C = PF_SO_COEF;
 
 struct SoArgs {
@@ -43,153 +42,237 @@ struct SoArgs {
     int64_t opitch, out_every;
 };
 
-struct SoMode {                            // what a thread knows about its mode
-    double k2, tstart, tsd;
-    int64_t fo_ts;
+// One stage slot of the coefficient table (48 bytes, 16-byte aligned): the host writes fotix as
+// a double (exact below 2^53), the kernels convert it once per use.
+struct SoStage {
+    double c1, R2, c2, fotix;             // + t, t/h in the slot's last 16 bytes (ramp only)
 };
 
-// source value of one stage as the right-hand side sees it: ramped (cosmomodels.py:925-944) and
-// NaN when the first-order result the reference would read there has not started yet
-__device__ __forceinline__ double stage_source(const SoArgs& a, const SoMode& m, const double* __restrict__ c,
-                                               double raw) {
-    double s = raw;
-    if (a.ramp) {
-        const double arg = c[3] - m.tstart - a.rb;
-        if (fabs(arg) < a.re) {
-            double r = (tanh(a.ra * arg) + a.rc) / a.rd;
-            if (m.tsd == c[5]) r = 0.0;                   // ramp[self.tstartindex == sotix] = 0
-            s = r * s;
-        }
-    }
-    if ((int64_t)c[4] < m.fo_ts) s = qnan();
+// p: shared memory (the solver) or global memory (single right-hand sides)
+__device__ __forceinline__ SoStage load_stage(const double* __restrict__ p) {
+    const double2 a = reinterpret_cast<const double2*>(p)[0];
+    const double2 b = reinterpret_cast<const double2*>(p)[1];
+    SoStage s;
+    s.c1 = a.x; s.R2 = a.y; s.c2 = b.x; s.fotix = b.y;
     return s;
 }
 
-// -( (3-eps) y1 + k^2 R2 y0 + c2 y0 + S )                       cosmomodels.py:754-755, 761-762
-__device__ __forceinline__ double so_accel(const double* __restrict__ c, double k2, double y0, double y1,
-                                           double s) {
-    double t = fma(c[2], y0, s);
-    t = fma(k2 * c[1], y0, t);
-    t = fma(c[0], y1, t);
-    return -t;
+// ramp factor of one stage (cosmomodels.py:925-944); 1 outside the ramp window.  Kept out of
+// line: it runs for ~1 e-fold per mode, and twelve inlined copies of tanh would bloat the loop.
+__device__ __noinline__ double ramp_factor(const double* __restrict__ slot, double tstart, double tsd, double ra,
+                                           double rb, double rc, double rd, double re) {
+    const double2 tt = reinterpret_cast<const double2*>(slot)[2];
+    const double t = tt.x, tdivh = tt.y;
+    const double arg = t - tstart - rb;
+    if (!(fabs(arg) < re)) return 1.0;
+    if (tsd == tdivh) return 0.0;                         // ramp[self.tstartindex == sotix] = 0
+    return (tanh(ra * arg) + rc) / rd;
 }
 
-__device__ __forceinline__ double load_src(const SoArgs& a, const double* __restrict__ c, int64_t kk, int part) {
-    if (!a.src) return 0.0;
-    const int64_t fotix = (int64_t)c[4];
-    return __ldg(a.src + 2 * (fotix * a.src_pitch + kk) + part);
+// 16-byte asynchronous copy global -> shared (LDGSTS, L2 only): completion is tracked by commit
+// groups, not by a register scoreboard, so a look-ahead of several steps costs no registers and a
+// consumer never waits on younger loads (the register-ring version did: profiles/r2c_so_ncu_notes.txt)
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
 
-__global__ void __launch_bounds__(SO_BLOCK) so_rk4_kernel(SoArgs a) {
+// y1' = -( c1 y1 + B y0 + S ),  B = k^2 R2 + c2                  cosmomodels.py:754-755, 761-762
+__device__ __forceinline__ double so_accel(double c1, double B, double y0, double y1, double s) {
+    return -fma(c1, y1, fma(B, y0, s));
+}
+
+// One thread per mode: both (Re, Im) pairs advance together (two independent dependency chains),
+// the stage coefficients, the ramp and the bookkeeping are shared between them.  A warp reads one
+// contiguous 512-byte piece of a source row per stage and writes four 256-byte pieces of result
+// rows per step.
+//
+// The coefficient table streams through shared memory in double-buffered chunks (1-D TMA bulk
+// copies + mbarrier, as the first-order kernels do with their records): every thread of the CTA
+// reads the same slot (broadcast), and -- what matters more -- those reads then wait on the
+// short scoreboard instead of sharing a long-scoreboard slot with source loads that are in
+// flight to HBM (ncu of the global-load version: two ~800-cycle stalls per step on L1-resident
+// coefficients, profiles/r2c_so_ncu_notes.txt).  All threads of a CTA walk the rows in step; a
+// mode that has not started yet only writes its NaN rows.
+constexpr int SO_CH = 30;                               // steps per chunk (multiple of SO_AHEAD)
+constexpr int SO_CHL = SO_CH + SO_AHEAD;                // + look-ahead slots for the source prefetch
+static_assert(SO_CH % SO_AHEAD == 0, "chunk must be a multiple of the look-ahead");
+
+__global__ void __launch_bounds__(SO_BLOCK, 8) so_rk4_kernel(SoArgs a) {
+    __shared__ __align__(128) double scoef[2][SO_CHL * 3 * SO_C];
+    __shared__ __align__(16) double2 sring[SO_AHEAD][3][SO_BLOCK];   // per-thread source look-ahead
+    __shared__ __align__(8) uint64_t bars[2];
+
     const int tid = threadIdx.x;
-    const int part = tid & 1;
-    const int64_t kk = (int64_t)blockIdx.x * (SO_BLOCK / 2) + (tid >> 1);
-    if (kk >= a.nk) return;
-    const int64_t op = a.opitch;
+    const int64_t kraw = (int64_t)blockIdx.x * SO_BLOCK + tid;
+    const bool live = kraw < a.nk;
+    const int64_t kk = live ? kraw : a.nk - 1;            // idle lanes shadow the last mode, store nothing
+    const int64_t op = a.opitch, nk = a.nk;
     const int64_t ts = a.tsix[kk];
-    SoMode m;
-    m.k2 = a.k[kk] * a.k[kk];
-    m.tstart = a.tstart ? a.tstart[kk] : 0.0;
-    m.tsd = (double)ts;
-    m.fo_ts = a.fo_tsix ? a.fo_tsix[kk] : INT64_MIN;
+    const double k2 = a.k[kk] * a.k[kk];
+    const double tstart = a.tstart ? a.tstart[kk] : 0.0;
+    const double tsd = (double)ts;
+    const double fo_ts = a.fo_tsix ? (double)a.fo_tsix[kk] : -1.0;
     const double h = a.h, hh = h * 0.5, h6 = h / 6.0;     // rk4.py:31-32
     const double nan = qnan();
 
-    int64_t next_out = (a.yout != nullptr && a.out_every > 0) ? a.t0 : INT64_MAX;
-    double* orow = a.yout ? a.yout + (2 * part) * op + kk : nullptr;   // this thread's two rows
-    auto advance_out = [&]() { next_out += a.out_every; orow += 4 * op; };
-
-    // rows before this mode's start stay NaN                       rk4.py:100
-    int64_t n = a.t0;
-    const int64_t pre_end = ts < a.t1 ? ts : a.t1;
-    if (next_out != INT64_MAX) {
-        // first output row at or after n is next_out (= t0): walk the output rows only
-        for (; next_out < pre_end; advance_out()) {
-            __stcs(orow, nan);
-            __stcs(orow + op, nan);
-        }
+    const int64_t nrows = a.t1 - a.t0;
+    const int64_t nchunks = (nrows + SO_CH - 1) / SO_CH;
+    auto issue = [&](int64_t c) {
+        const int buf = (int)(c & 1);
+        const int64_t base = a.t0 + c * SO_CH;
+        const int64_t cnt = (a.T - base) < SO_CHL ? (a.T - base) : SO_CHL;
+        const uint32_t bytes = (uint32_t)(cnt * 3 * SO_C * sizeof(double));
+        mbar_expect_tx(&bars[buf], bytes);
+        bulk_g2s(&scoef[buf][0], a.coef + base * 3 * SO_C, bytes, &bars[buf]);
+    };
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (ts >= a.t1) return;
-    n = ts > a.t0 ? ts : a.t0;
-
-    double y0, y1;
-    if (n == ts) {                                        // the start row is ystart[:, k] itself
-        y0 = a.ystart[(2 * part) * a.nk + kk];
-        y1 = a.ystart[(2 * part + 1) * a.nk + kk];
-    } else {                                              // resume a windowed run
-        y0 = a.state[(2 * part) * a.nk + kk];
-        y1 = a.state[(2 * part + 1) * a.nk + kk];
+    __syncthreads();
+    if (tid == 0) {
+        if (nchunks > 0) issue(0);
+        if (nchunks > 1) issue(1);
     }
 
-    // steps n -> n+1 are taken for n in [n, nstep_end)
+    int64_t next_out = (a.yout != nullptr && a.out_every > 0 && live) ? a.t0 : INT64_MAX;
+    double* orow = a.yout ? a.yout + kk : nullptr;
+
+    double yr0 = 0.0, yr1 = 0.0, yi0 = 0.0, yi1 = 0.0;    // (Re d2, Re d2'), (Im d2, Im d2')
+    if (a.t0 > ts) {                                      // resume a windowed run
+        yr0 = a.state[kk]; yr1 = a.state[nk + kk]; yi0 = a.state[2 * nk + kk]; yi1 = a.state[3 * nk + kk];
+    }
+    // the ramp can only be active for steps in [ramp_lo, ramp_hi] (stage times within re of
+    // tstart + rb; two steps of slack on either side), checked exactly inside
+    int64_t ramp_lo = INT64_MAX, ramp_hi = INT64_MIN;
+    if (a.ramp) {
+        const double x0 = __ldg(a.coef + 4);              // t of step 0, stage 0 = simtstart
+        const double c = tstart + a.rb - x0;
+        const double lo = floor((c - a.re) / h) - 2.0, hi = ceil((c + a.re) / h) + 2.0;
+        ramp_lo = lo < -9e18 ? INT64_MIN : (lo > 9e18 ? INT64_MAX : (int64_t)lo);
+        ramp_hi = hi > 9e18 ? INT64_MAX : (hi < -9e18 ? INT64_MIN : (int64_t)hi);
+        if (!(c == c)) { ramp_lo = INT64_MIN; ramp_hi = INT64_MAX; }
+    }
+    // steps q -> q+1 are taken for q in [max(ts, t0), nstep_end)
     const int64_t nstep_end = (a.t1 < a.T - 1) ? a.t1 : a.T - 1;
-    double ring[SO_AHEAD][3];
+    const int64_t first = ts > a.t0 ? ts : a.t0;
+    const double2* __restrict__ srcbase = reinterpret_cast<const double2*>(a.src) + kk;
+    // source values of step q's three stages -> this thread's ring slot; always one commit group
+    auto prefetch = [&](int slot, const double* cslot, int64_t q) {
+        if (a.src && q >= first && q < nstep_end) {
 #pragma unroll
-    for (int j = 0; j < SO_AHEAD; ++j) {
-        const int64_t q = n + j;
-#pragma unroll
-        for (int s = 0; s < 3; ++s)
-            ring[j][s] = (q < nstep_end) ? load_src(a, a.coef + (q * 3 + s) * SO_C, kk, part) : 0.0;
-    }
+            for (int s = 0; s < 3; ++s)
+                cp_async16(&sring[slot][s][tid], srcbase + (int64_t)cslot[s * SO_C + 3] * a.src_pitch);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
 
-    for (; n < a.t1; n += SO_AHEAD) {
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int buf = (int)(c & 1);
+        mbar_wait(&bars[buf], (uint32_t)((c >> 1) & 1));
+        const double* __restrict__ sc = &scoef[buf][0];
+        const int64_t base = a.t0 + c * SO_CH;
+        const int cnt = (int)((a.t1 - base) < SO_CH ? (a.t1 - base) : SO_CH);
+        if (c == 0) {
 #pragma unroll
-        for (int j = 0; j < SO_AHEAD; ++j) {
-            const int64_t q = n + j;
-            if (q >= a.t1) break;
-            if (q == next_out) {
-                __stcs(orow, y0);
-                __stcs(orow + op, y1);
-                advance_out();
-            }
-            if (q < nstep_end) {
-                const double* __restrict__ c = a.coef + q * 3 * SO_C;
-                const double s0 = stage_source(a, m, c, ring[j][0]);
-                const double s1 = stage_source(a, m, c + SO_C, ring[j][1]);
-                const double s2 = stage_source(a, m, c + 2 * SO_C, ring[j][2]);
-                // refill this slot with the values of step q + SO_AHEAD
-                const int64_t qa = q + SO_AHEAD;
+            for (int j = 0; j < SO_AHEAD; ++j) prefetch(j, sc + j * 3 * SO_C, base + j);
+        }
+        for (int i = 0; i < cnt; i += SO_AHEAD) {
 #pragma unroll
-                for (int s = 0; s < 3; ++s)
-                    ring[j][s] = (qa < nstep_end) ? load_src(a, a.coef + (qa * 3 + s) * SO_C, kk, part) : 0.0;
-                // one classical RK4 step, operation order of rk4.py:27-55
-                const double d0 = y1, d1 = so_accel(c, m.k2, y0, y1, s0);
-                double u0 = fma(hh, d0, y0), u1 = fma(hh, d1, y1);
-                const double e0 = u1, e1 = so_accel(c + SO_C, m.k2, u0, u1, s1);          // dyt
-                u0 = fma(hh, e0, y0); u1 = fma(hh, e1, y1);
-                double f0 = u1, f1 = so_accel(c + SO_C, m.k2, u0, u1, s1);                // dym
-                u0 = fma(h, f0, y0); u1 = fma(h, f1, y1);
-                f0 += e0; f1 += e1;
-                const double g0 = u1, g1 = so_accel(c + 2 * SO_C, m.k2, u0, u1, s2);
-                y0 = fma(h6, d0 + g0 + 2.0 * f0, y0);
-                y1 = fma(h6, d1 + g1 + 2.0 * f1, y1);
+            for (int j = 0; j < SO_AHEAD; ++j) {
+                const int64_t q = base + i + j;
+                if (i + j >= cnt) break;
+                const double* __restrict__ cq = sc + (i + j) * 3 * SO_C;
+                if (q == ts) {                            // the start row is ystart[:, k] itself
+                    yr0 = a.ystart[kk]; yr1 = a.ystart[nk + kk];
+                    yi0 = a.ystart[2 * nk + kk]; yi1 = a.ystart[3 * nk + kk];
+                }
+                if (q == next_out) {                      // rows before the start stay NaN, rk4.py:100
+                    const bool pre = q < ts;
+                    __stcs(orow, pre ? nan : yr0);
+                    __stcs(orow + op, pre ? nan : yr1);
+                    __stcs(orow + 2 * op, pre ? nan : yi0);
+                    __stcs(orow + 3 * op, pre ? nan : yi1);
+                    next_out += a.out_every;
+                    orow += 4 * op;
+                }
+                const bool stepping = q >= first && q < nstep_end;
+                // this step's source values have landed when at most SO_AHEAD - 1 younger groups
+                // are still pending
+                asm volatile("cp.async.wait_group %0;" ::"n"(SO_AHEAD - 1) : "memory");
+                double2 s0 = make_double2(0.0, 0.0), s1 = s0, s2 = s0;
+                if (stepping && a.src) { s0 = sring[j][0][tid]; s1 = sring[j][1][tid]; s2 = sring[j][2][tid]; }
+                // refill the slot with the source values of step q + SO_AHEAD (its coefficients are
+                // inside this chunk's SO_CHL steps)
+                prefetch(j, cq + SO_AHEAD * 3 * SO_C, q + SO_AHEAD);
+                if (stepping) {
+                    const SoStage c0 = load_stage(cq), c1 = load_stage(cq + SO_C), c2 = load_stage(cq + 2 * SO_C);
+                    if (q >= ramp_lo && q <= ramp_hi) {
+                        const double r0 = ramp_factor(cq, tstart, tsd, a.ra, a.rb, a.rc, a.rd, a.re);
+                        const double r1 = ramp_factor(cq + SO_C, tstart, tsd, a.ra, a.rb, a.rc, a.rd, a.re);
+                        const double r2 = ramp_factor(cq + 2 * SO_C, tstart, tsd, a.ra, a.rb, a.rc, a.rd, a.re);
+                        if (r0 != 1.0) { s0.x = r0 * s0.x; s0.y = r0 * s0.y; }
+                        if (r1 != 1.0) { s1.x = r1 * s1.x; s1.y = r1 * s1.y; }
+                        if (r2 != 1.0) { s2.x = r2 * s2.x; s2.y = r2 * s2.y; }
+                    }
+                    // a stage that reads the first-order result before this mode's first-order
+                    // start sees NaN there in the reference
+                    if (c0.fotix < fo_ts) {
+                        s0 = make_double2(nan, nan);
+                        if (c1.fotix < fo_ts) s1 = s0;
+                        if (c2.fotix < fo_ts) s2 = s0;
+                    }
+                    const double B0 = fma(k2, c0.R2, c0.c2), B1 = fma(k2, c1.R2, c1.c2), B2 = fma(k2, c2.R2, c2.c2);
+                    // one classical RK4 step, operation order of rk4.py:27-55, for both pairs
+                    const double dr = so_accel(c0.c1, B0, yr0, yr1, s0.x), di = so_accel(c0.c1, B0, yi0, yi1, s0.y);
+                    double ur0 = fma(hh, yr1, yr0), ur1 = fma(hh, dr, yr1);
+                    double ui0 = fma(hh, yi1, yi0), ui1 = fma(hh, di, yi1);
+                    const double er0 = ur1, er1 = so_accel(c1.c1, B1, ur0, ur1, s1.x);      // dyt
+                    const double ei0 = ui1, ei1 = so_accel(c1.c1, B1, ui0, ui1, s1.y);
+                    ur0 = fma(hh, er0, yr0); ur1 = fma(hh, er1, yr1);
+                    ui0 = fma(hh, ei0, yi0); ui1 = fma(hh, ei1, yi1);
+                    double fr0 = ur1, fr1 = so_accel(c1.c1, B1, ur0, ur1, s1.x);            // dym
+                    double fi0 = ui1, fi1 = so_accel(c1.c1, B1, ui0, ui1, s1.y);
+                    ur0 = fma(h, fr0, yr0); ur1 = fma(h, fr1, yr1);
+                    ui0 = fma(h, fi0, yi0); ui1 = fma(h, fi1, yi1);
+                    fr0 += er0; fr1 += er1; fi0 += ei0; fi1 += ei1;
+                    const double gr1 = so_accel(c2.c1, B2, ur0, ur1, s2.x), gi1 = so_accel(c2.c1, B2, ui0, ui1, s2.y);
+                    yr0 = fma(h6, yr1 + ur1 + 2.0 * fr0, yr0);
+                    yi0 = fma(h6, yi1 + ui1 + 2.0 * fi0, yi0);
+                    yr1 = fma(h6, dr + gr1 + 2.0 * fr1, yr1);
+                    yi1 = fma(h6, di + gi1 + 2.0 * fi1, yi1);
+                }
             }
         }
+        __syncthreads();                                  // everyone is done reading scoef[buf]
+        if (tid == 0 && c + 2 < nchunks) issue(c + 2);
     }
-    if (a.state) {
-        a.state[(2 * part) * a.nk + kk] = y0;
-        a.state[(2 * part + 1) * a.nk + kk] = y1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (live && a.state && ts < a.t1) {
+        a.state[kk] = yr0; a.state[nk + kk] = yr1; a.state[2 * nk + kk] = yi0; a.state[3 * nk + kk] = yi1;
     }
 }
 
-// one right-hand side: dydx[4][nk] = derivs(y[4][nk], t) with the stage coefficients in c
+// one right-hand side: dydx[4][nk] = derivs(y[4][nk], t) with the stage coefficients in a.coef
 __global__ void so_derivs_kernel(SoArgs a, const double* __restrict__ y, const double* __restrict__ srcrow,
                                  double* __restrict__ dydx) {
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int part = (int)(gid & 1);
-    const int64_t kk = gid >> 1;
+    const int64_t kk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (kk >= a.nk) return;
-    SoMode m;
-    m.k2 = a.k[kk] * a.k[kk];
-    m.tstart = a.tstart ? a.tstart[kk] : 0.0;
-    m.tsd = a.tsix ? (double)a.tsix[kk] : -1.0;
-    m.fo_ts = a.fo_tsix ? a.fo_tsix[kk] : INT64_MIN;
-    const double* c = a.coef;
-    const double raw = srcrow ? srcrow[2 * kk + part] : 0.0;
-    const double s = stage_source(a, m, c, raw);
-    const double y0 = y[(2 * part) * a.nk + kk], y1 = y[(2 * part + 1) * a.nk + kk];
-    dydx[(2 * part) * a.nk + kk] = y1;                                   // cosmomodels.py:751, 758
-    dydx[(2 * part + 1) * a.nk + kk] = so_accel(c, m.k2, y0, y1, s);
+    const int64_t nk = a.nk;
+    const SoStage c = load_stage(a.coef);
+    const double k2 = a.k[kk] * a.k[kk];
+    double2 s = srcrow ? reinterpret_cast<const double2*>(srcrow)[kk] : make_double2(0.0, 0.0);
+    if (a.ramp) {
+        const double r = ramp_factor(a.coef, a.tstart[kk], (double)a.tsix[kk], a.ra, a.rb, a.rc, a.rd, a.re);
+        if (r != 1.0) { s.x = r * s.x; s.y = r * s.y; }
+    }
+    if (a.fo_tsix && c.fotix < (double)a.fo_tsix[kk]) s = make_double2(qnan(), qnan());
+    const double B = fma(k2, c.R2, c.c2);
+    dydx[kk] = y[nk + kk];                                               // cosmomodels.py:751
+    dydx[nk + kk] = so_accel(c.c1, B, y[kk], y[nk + kk], s.x);
+    dydx[2 * nk + kk] = y[3 * nk + kk];                                  // :758
+    dydx[3 * nk + kk] = so_accel(c.c1, B, y[2 * nk + kk], y[3 * nk + kk], s.y);
 }
 
 static int fill_ramp(SoArgs& a, const double* ramp_host, const double* tstart_dev, const char* who) {
@@ -236,8 +319,7 @@ extern "C" int pf_so_run(int64_t nk, const double* k_dev, const int64_t* tsix_de
     a.T = T; a.t0 = t0; a.t1 = t1; a.h = h; a.state = state_dev;
     a.yout = out_every > 0 ? yout_dev : nullptr; a.out_every = out_every;
     a.opitch = out_pitch ? out_pitch : nk;
-    const int kpb = SO_BLOCK / 2;
-    so_rk4_kernel<<<(unsigned)((nk + kpb - 1) / kpb), SO_BLOCK, 0, (cudaStream_t)stream>>>(a);
+    so_rk4_kernel<<<(unsigned)((nk + SO_BLOCK - 1) / SO_BLOCK), SO_BLOCK, 0, (cudaStream_t)stream>>>(a);
     PF_CUDA_CHECK(cudaGetLastError(), "pf_so_run launch");
     return PF_OK;
 }
@@ -255,7 +337,7 @@ extern "C" int pf_so_derivs(int64_t nk, const double* k_dev, const int64_t* tsix
     if (rc) return rc;
     if (a.ramp && !tsix_dev) { set_error("pf_so_derivs: a ramp needs tsix_dev"); return PF_E_ARG; }
     const int block = 128;
-    so_derivs_kernel<<<(unsigned)((2 * nk + block - 1) / block), block, 0, (cudaStream_t)stream>>>(
+    so_derivs_kernel<<<(unsigned)((nk + block - 1) / block), block, 0, (cudaStream_t)stream>>>(
         a, y_dev, source_row_dev, dydx_dev);
     PF_CUDA_CHECK(cudaGetLastError(), "pf_so_derivs launch");
     return PF_OK;
