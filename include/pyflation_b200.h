@@ -250,7 +250,7 @@ int pf_scatter_slab(int64_t nrows_times_nvar, int64_t nk_r, int64_t nk, int64_t 
  *   coef_dev[T][3][PF_SO_COEF]: for step n -> n+1 and its three stage times t = simtstart + n h,
  *     + h/2, + h (rk4.py:27-55, 116-118):  3 - eps,  1/(a H)^2,  V''/H^2 - 3 phi'^2,
  *     fotix = around((t - fo_simtstart)/fo_step) (row of the first-order time grid the reference
- *     reads at this stage, :724; stored as a double),  t,  t/h (compared with the start row by
+ *     reads at this stage, :724; an int64 in this 8-byte word),  t,  t/h (compared with the start row by
  *     the ramp, :935-937);  eps, H, phi', V'' taken at row fotix of the first-order / background
  *     result.  16-byte aligned.
  *   source_dev c128 [source_rows][source_pitch]: the source term on the first-order time grid,

@@ -42,10 +42,11 @@ struct SoArgs {
     int64_t opitch, out_every;
 };
 
-// One stage slot of the coefficient table (48 bytes, 16-byte aligned): the host writes fotix as
-// a double (exact below 2^53), the kernels convert it once per use.
+// One stage slot of the coefficient table (48 bytes, 16-byte aligned); fotix is an int64 stored in
+// the slot's fourth 8-byte word (no fp64 -> integer conversion on the device).
 struct SoStage {
-    double c1, R2, c2, fotix;             // + t, t/h in the slot's last 16 bytes (ramp only)
+    double c1, R2, c2;
+    int64_t fotix;                        // + t, t/h in the slot's last 16 bytes (ramp only)
 };
 
 // p: shared memory (the solver) or global memory (single right-hand sides)
@@ -53,7 +54,7 @@ __device__ __forceinline__ SoStage load_stage(const double* __restrict__ p) {
     const double2 a = reinterpret_cast<const double2*>(p)[0];
     const double2 b = reinterpret_cast<const double2*>(p)[1];
     SoStage s;
-    s.c1 = a.x; s.R2 = a.y; s.c2 = b.x; s.fotix = b.y;
+    s.c1 = a.x; s.R2 = a.y; s.c2 = b.x; s.fotix = __double_as_longlong(b.y);
     return s;
 }
 
@@ -79,6 +80,32 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 // y1' = -( c1 y1 + B y0 + S ),  B = k^2 R2 + c2                  cosmomodels.py:754-755, 761-762
 __device__ __forceinline__ double so_accel(double c1, double B, double y0, double y1, double s) {
     return -fma(c1, y1, fma(B, y0, s));
+}
+
+struct SoState { double yr0, yr1, yi0, yi1; };          // (Re d2, Re d2'), (Im d2, Im d2')
+
+// one classical RK4 step, operation order of rk4.py:27-55, for both pairs
+__device__ __forceinline__ void so_step(SoState& y, const SoStage& c0, const SoStage& c1, const SoStage& c2,
+                                        double k2, double2 s0, double2 s1, double2 s2, double h, double hh,
+                                        double h6) {
+    const double B0 = fma(k2, c0.R2, c0.c2), B1 = fma(k2, c1.R2, c1.c2), B2 = fma(k2, c2.R2, c2.c2);
+    const double dr = so_accel(c0.c1, B0, y.yr0, y.yr1, s0.x), di = so_accel(c0.c1, B0, y.yi0, y.yi1, s0.y);
+    double ur0 = fma(hh, y.yr1, y.yr0), ur1 = fma(hh, dr, y.yr1);
+    double ui0 = fma(hh, y.yi1, y.yi0), ui1 = fma(hh, di, y.yi1);
+    const double er0 = ur1, er1 = so_accel(c1.c1, B1, ur0, ur1, s1.x);      // dyt
+    const double ei0 = ui1, ei1 = so_accel(c1.c1, B1, ui0, ui1, s1.y);
+    ur0 = fma(hh, er0, y.yr0); ur1 = fma(hh, er1, y.yr1);
+    ui0 = fma(hh, ei0, y.yi0); ui1 = fma(hh, ei1, y.yi1);
+    double fr0 = ur1, fr1 = so_accel(c1.c1, B1, ur0, ur1, s1.x);            // dym
+    double fi0 = ui1, fi1 = so_accel(c1.c1, B1, ui0, ui1, s1.y);
+    ur0 = fma(h, fr0, y.yr0); ur1 = fma(h, fr1, y.yr1);
+    ui0 = fma(h, fi0, y.yi0); ui1 = fma(h, fi1, y.yi1);
+    fr0 += er0; fr1 += er1; fi0 += ei0; fi1 += ei1;
+    const double gr1 = so_accel(c2.c1, B2, ur0, ur1, s2.x), gi1 = so_accel(c2.c1, B2, ui0, ui1, s2.y);
+    y.yr0 = fma(h6, y.yr1 + ur1 + 2.0 * fr0, y.yr0);
+    y.yi0 = fma(h6, y.yi1 + ui1 + 2.0 * fi0, y.yi0);
+    y.yr1 = fma(h6, dr + gr1 + 2.0 * fr1, y.yr1);
+    y.yi1 = fma(h6, di + gi1 + 2.0 * fi1, y.yi1);
 }
 
 // One thread per mode: both (Re, Im) pairs advance together (two independent dependency chains),
@@ -111,7 +138,7 @@ __global__ void __launch_bounds__(SO_BLOCK, 8) so_rk4_kernel(SoArgs a) {
     const double k2 = a.k[kk] * a.k[kk];
     const double tstart = a.tstart ? a.tstart[kk] : 0.0;
     const double tsd = (double)ts;
-    const double fo_ts = a.fo_tsix ? (double)a.fo_tsix[kk] : -1.0;
+    const int64_t fo_ts = a.fo_tsix ? a.fo_tsix[kk] : INT64_MIN;
     const double h = a.h, hh = h * 0.5, h6 = h / 6.0;     // rk4.py:31-32
     const double nan = qnan();
 
@@ -139,9 +166,9 @@ __global__ void __launch_bounds__(SO_BLOCK, 8) so_rk4_kernel(SoArgs a) {
     int64_t next_out = (a.yout != nullptr && a.out_every > 0 && live) ? a.t0 : INT64_MAX;
     double* orow = a.yout ? a.yout + kk : nullptr;
 
-    double yr0 = 0.0, yr1 = 0.0, yi0 = 0.0, yi1 = 0.0;    // (Re d2, Re d2'), (Im d2, Im d2')
+    SoState y = {0.0, 0.0, 0.0, 0.0};
     if (a.t0 > ts) {                                      // resume a windowed run
-        yr0 = a.state[kk]; yr1 = a.state[nk + kk]; yi0 = a.state[2 * nk + kk]; yi1 = a.state[3 * nk + kk];
+        y.yr0 = a.state[kk]; y.yr1 = a.state[nk + kk]; y.yi0 = a.state[2 * nk + kk]; y.yi1 = a.state[3 * nk + kk];
     }
     // the ramp can only be active for steps in [ramp_lo, ramp_hi] (stage times within re of
     // tstart + rb; two steps of slack on either side), checked exactly inside
@@ -163,7 +190,7 @@ __global__ void __launch_bounds__(SO_BLOCK, 8) so_rk4_kernel(SoArgs a) {
         if (a.src && q >= first && q < nstep_end) {
 #pragma unroll
             for (int s = 0; s < 3; ++s)
-                cp_async16(&sring[slot][s][tid], srcbase + (int64_t)cslot[s * SO_C + 3] * a.src_pitch);
+                cp_async16(&sring[slot][s][tid], srcbase + __double_as_longlong(cslot[s * SO_C + 3]) * a.src_pitch);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -179,21 +206,55 @@ __global__ void __launch_bounds__(SO_BLOCK, 8) so_rk4_kernel(SoArgs a) {
             for (int j = 0; j < SO_AHEAD; ++j) prefetch(j, sc + j * 3 * SO_C, base + j);
         }
         for (int i = 0; i < cnt; i += SO_AHEAD) {
+            // Steady state (almost every step of a full-trajectory run): the mode is running, the
+            // ramp window is behind it, every row is stored and the look-ahead stays inside the
+            // run -- the same step with none of the per-row decisions.
+            const int64_t q0 = base + i;
+            if (i + SO_AHEAD <= cnt && q0 > ts && q0 > ramp_hi && q0 >= first && a.out_every == 1 &&
+                next_out == q0 && q0 + 2 * SO_AHEAD <= nstep_end && a.src) {
+#pragma unroll
+                for (int j = 0; j < SO_AHEAD; ++j) {
+                    const double* __restrict__ cq = sc + (i + j) * 3 * SO_C;
+                    __stcs(orow, y.yr0);
+                    __stcs(orow + op, y.yr1);
+                    __stcs(orow + 2 * op, y.yi0);
+                    __stcs(orow + 3 * op, y.yi1);
+                    orow += 4 * op;
+                    asm volatile("cp.async.wait_group %0;" ::"n"(SO_AHEAD - 1) : "memory");
+                    double2 s0 = sring[j][0][tid], s1 = sring[j][1][tid], s2 = sring[j][2][tid];
+                    {
+                        const double* __restrict__ ca = cq + SO_AHEAD * 3 * SO_C;
+#pragma unroll
+                        for (int s = 0; s < 3; ++s)
+                            cp_async16(&sring[j][s][tid], srcbase + __double_as_longlong(ca[s * SO_C + 3]) * a.src_pitch);
+                        asm volatile("cp.async.commit_group;" ::: "memory");
+                    }
+                    const SoStage c0 = load_stage(cq), c1 = load_stage(cq + SO_C), c2 = load_stage(cq + 2 * SO_C);
+                    if (c0.fotix < fo_ts) {               // see below
+                        s0 = make_double2(nan, nan);
+                        if (c1.fotix < fo_ts) s1 = s0;
+                        if (c2.fotix < fo_ts) s2 = s0;
+                    }
+                    so_step(y, c0, c1, c2, k2, s0, s1, s2, h, hh, h6);
+                }
+                next_out += SO_AHEAD;
+                continue;
+            }
 #pragma unroll
             for (int j = 0; j < SO_AHEAD; ++j) {
                 const int64_t q = base + i + j;
                 if (i + j >= cnt) break;
                 const double* __restrict__ cq = sc + (i + j) * 3 * SO_C;
                 if (q == ts) {                            // the start row is ystart[:, k] itself
-                    yr0 = a.ystart[kk]; yr1 = a.ystart[nk + kk];
-                    yi0 = a.ystart[2 * nk + kk]; yi1 = a.ystart[3 * nk + kk];
+                    y.yr0 = a.ystart[kk]; y.yr1 = a.ystart[nk + kk];
+                    y.yi0 = a.ystart[2 * nk + kk]; y.yi1 = a.ystart[3 * nk + kk];
                 }
                 if (q == next_out) {                      // rows before the start stay NaN, rk4.py:100
                     const bool pre = q < ts;
-                    __stcs(orow, pre ? nan : yr0);
-                    __stcs(orow + op, pre ? nan : yr1);
-                    __stcs(orow + 2 * op, pre ? nan : yi0);
-                    __stcs(orow + 3 * op, pre ? nan : yi1);
+                    __stcs(orow, pre ? nan : y.yr0);
+                    __stcs(orow + op, pre ? nan : y.yr1);
+                    __stcs(orow + 2 * op, pre ? nan : y.yi0);
+                    __stcs(orow + 3 * op, pre ? nan : y.yi1);
                     next_out += a.out_every;
                     orow += 4 * op;
                 }
@@ -223,25 +284,7 @@ __global__ void __launch_bounds__(SO_BLOCK, 8) so_rk4_kernel(SoArgs a) {
                         if (c1.fotix < fo_ts) s1 = s0;
                         if (c2.fotix < fo_ts) s2 = s0;
                     }
-                    const double B0 = fma(k2, c0.R2, c0.c2), B1 = fma(k2, c1.R2, c1.c2), B2 = fma(k2, c2.R2, c2.c2);
-                    // one classical RK4 step, operation order of rk4.py:27-55, for both pairs
-                    const double dr = so_accel(c0.c1, B0, yr0, yr1, s0.x), di = so_accel(c0.c1, B0, yi0, yi1, s0.y);
-                    double ur0 = fma(hh, yr1, yr0), ur1 = fma(hh, dr, yr1);
-                    double ui0 = fma(hh, yi1, yi0), ui1 = fma(hh, di, yi1);
-                    const double er0 = ur1, er1 = so_accel(c1.c1, B1, ur0, ur1, s1.x);      // dyt
-                    const double ei0 = ui1, ei1 = so_accel(c1.c1, B1, ui0, ui1, s1.y);
-                    ur0 = fma(hh, er0, yr0); ur1 = fma(hh, er1, yr1);
-                    ui0 = fma(hh, ei0, yi0); ui1 = fma(hh, ei1, yi1);
-                    double fr0 = ur1, fr1 = so_accel(c1.c1, B1, ur0, ur1, s1.x);            // dym
-                    double fi0 = ui1, fi1 = so_accel(c1.c1, B1, ui0, ui1, s1.y);
-                    ur0 = fma(h, fr0, yr0); ur1 = fma(h, fr1, yr1);
-                    ui0 = fma(h, fi0, yi0); ui1 = fma(h, fi1, yi1);
-                    fr0 += er0; fr1 += er1; fi0 += ei0; fi1 += ei1;
-                    const double gr1 = so_accel(c2.c1, B2, ur0, ur1, s2.x), gi1 = so_accel(c2.c1, B2, ui0, ui1, s2.y);
-                    yr0 = fma(h6, yr1 + ur1 + 2.0 * fr0, yr0);
-                    yi0 = fma(h6, yi1 + ui1 + 2.0 * fi0, yi0);
-                    yr1 = fma(h6, dr + gr1 + 2.0 * fr1, yr1);
-                    yi1 = fma(h6, di + gi1 + 2.0 * fi1, yi1);
+                    so_step(y, c0, c1, c2, k2, s0, s1, s2, h, hh, h6);
                 }
             }
         }
@@ -250,7 +293,7 @@ __global__ void __launch_bounds__(SO_BLOCK, 8) so_rk4_kernel(SoArgs a) {
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (live && a.state && ts < a.t1) {
-        a.state[kk] = yr0; a.state[nk + kk] = yr1; a.state[2 * nk + kk] = yi0; a.state[3 * nk + kk] = yi1;
+        a.state[kk] = y.yr0; a.state[nk + kk] = y.yr1; a.state[2 * nk + kk] = y.yi0; a.state[3 * nk + kk] = y.yi1;
     }
 }
 
@@ -267,7 +310,7 @@ __global__ void so_derivs_kernel(SoArgs a, const double* __restrict__ y, const d
         const double r = ramp_factor(a.coef, a.tstart[kk], (double)a.tsix[kk], a.ra, a.rb, a.rc, a.rd, a.re);
         if (r != 1.0) { s.x = r * s.x; s.y = r * s.y; }
     }
-    if (a.fo_tsix && c.fotix < (double)a.fo_tsix[kk]) s = make_double2(qnan(), qnan());
+    if (a.fo_tsix && c.fotix < a.fo_tsix[kk]) s = make_double2(qnan(), qnan());
     const double B = fma(k2, c.R2, c.c2);
     dydx[kk] = y[nk + kk];                                               // cosmomodels.py:751
     dydx[nk + kk] = so_accel(c.c1, B, y[kk], y[nk + kk], s.x);

@@ -605,7 +605,7 @@ def derivs_device(model, y, t, k=None):
 # ---- second-order stage (K9) ------------------------------------------------------------------
 def so_stage_coefficients(model, t, fo_bg0, bgepsilon, fo_simtstart, fo_tstep, so_tstep, device=None):
     """The time-only factors of the second-order right-hand side at the times ``t`` (any shape):
-    array t.shape + (PF_SO_COEF,) of  3 - eps,  1/(aH)^2,  V''/H^2 - 3 phi'^2,  fotix,  t,  t/h
+    array t.shape + (PF_SO_COEF,) of  3 - eps,  1/(aH)^2,  V''/H^2 - 3 phi'^2,  fotix (int64 bits),  t,  t/h
     (cosmomodels.py:724-755), with eps, phi', H, V'' read at row fotix of the first-order result
     (``fo_bg0`` [T_fo, 3]: column 0's phi, phi', H) / of ``bgepsilon``.  V'' is evaluated on the
     device (K0) for every first-order row once."""
@@ -626,7 +626,7 @@ def so_stage_coefficients(model, t, fo_bg0, bgepsilon, fo_simtstart, fo_tstep, s
         coef[..., 0] = 3 - np.asarray(bgepsilon, dtype=np.float64)[fotix]
         coef[..., 1] = 1.0 / (a * H) ** 2
         coef[..., 2] = d2U[fotix] / H ** 2 - 3 * (phidot ** 2)
-        coef[..., 3] = fotix
+        coef[..., 3] = fotix.view(np.float64)                                   # int64 bits, not a double
         coef[..., 4] = t
         coef[..., 5] = t / so_tstep                                             # :935
     return coef
@@ -678,7 +678,7 @@ class SecondOrderProblem(object):
                     src = up(np.ascontiguousarray(src, dtype=np.complex128))
                 if src.dtype != torch.complex128 or src.dim() != 2 or src.shape[1] != nk:
                     raise ValueError("source must be complex128 of shape (T_fo, len(k))")
-                if int(coef[: max(self.T - 1, 1), :, 3].max()) >= src.shape[0]:
+                if int(coef[: max(self.T - 1, 1), :, 3].view(np.int64).max()) >= src.shape[0]:
                     raise IndexError("second-order stage time outside the source term")
                 self.source = src.contiguous()
             self.state = torch.zeros((4, nk), dtype=torch.float64, device=self.dev)
