@@ -12,15 +12,24 @@
 // Everything except k and S is a function of the stage time alone, so the host tabulates it once
 // per run ("coefficients": three stage times per step, PF_SO_COEF doubles each) and the kernel
 // is what remains: one thread per mode, 32 B of source read and 32 B of result written per mode
-// and step -- HBM-bound.  The source values of the next PF_SO_AHEAD steps are loaded into registers before they are
+// and step -- HBM-bound.  The source values of the next SO_AHEAD steps are copied into shared memory before they are
 // needed (they do not depend on the state), which is what keeps enough bytes in flight.
 #include "pf_common.cuh"
 #include "pf_fo_shared.cuh"
 
 namespace pf {
 
-constexpr int SO_BLOCK = 64;
-constexpr int SO_AHEAD = 6;          // steps of source values held in registers ahead of the RK4
+#ifndef PF_SO_BLOCK
+#define PF_SO_BLOCK 64
+#endif
+#ifndef PF_SO_AHEAD
+#define PF_SO_AHEAD 4
+#endif
+#ifndef PF_SO_MINB
+#define PF_SO_MINB 8
+#endif
+constexpr int SO_BLOCK = PF_SO_BLOCK;
+constexpr int SO_AHEAD = PF_SO_AHEAD;          // steps of source look-ahead (cp.async ring)
 constexpr int SO_C = PF_SO_COEF;
 
 struct SoArgs {
@@ -120,11 +129,11 @@ __device__ __forceinline__ void so_step(SoState& y, const SoStage& c0, const SoS
 // flight to HBM (ncu of the global-load version: two ~800-cycle stalls per step on L1-resident
 // coefficients, profiles/r2c_so_ncu_notes.txt).  All threads of a CTA walk the rows in step; a
 // mode that has not started yet only writes its NaN rows.
-constexpr int SO_CH = 30;                               // steps per chunk (multiple of SO_AHEAD)
+constexpr int SO_CH = (30 / SO_AHEAD) * SO_AHEAD;       // steps per chunk (multiple of SO_AHEAD)
 constexpr int SO_CHL = SO_CH + SO_AHEAD;                // + look-ahead slots for the source prefetch
 static_assert(SO_CH % SO_AHEAD == 0, "chunk must be a multiple of the look-ahead");
 
-__global__ void __launch_bounds__(SO_BLOCK, 8) so_rk4_kernel(SoArgs a) {
+__global__ void __launch_bounds__(SO_BLOCK, PF_SO_MINB) so_rk4_kernel(SoArgs a) {
     __shared__ __align__(128) double scoef[2][SO_CHL * 3 * SO_C];
     __shared__ __align__(16) double2 sring[SO_AHEAD][3][SO_BLOCK];   // per-thread source look-ahead
     __shared__ __align__(8) uint64_t bars[2];
@@ -212,9 +221,16 @@ __global__ void __launch_bounds__(SO_BLOCK, 8) so_rk4_kernel(SoArgs a) {
             const int64_t q0 = base + i;
             if (i + SO_AHEAD <= cnt && q0 > ts && q0 > ramp_hi && q0 >= first && a.out_every == 1 &&
                 next_out == q0 && q0 + 2 * SO_AHEAD <= nstep_end && a.src) {
+                // the coefficients of step j + 1 are read while step j computes (the asm statements
+                // below are compiler barriers: without this every step would start with an exposed
+                // shared-memory round trip)
+                const double* __restrict__ cb = sc + i * 3 * SO_C;
+                SoStage c0 = load_stage(cb), c1 = load_stage(cb + SO_C), c2 = load_stage(cb + 2 * SO_C);
 #pragma unroll
                 for (int j = 0; j < SO_AHEAD; ++j) {
-                    const double* __restrict__ cq = sc + (i + j) * 3 * SO_C;
+                    const double* __restrict__ cq = cb + j * 3 * SO_C;
+                    const SoStage n0 = load_stage(cq + 3 * SO_C), n1 = load_stage(cq + 4 * SO_C),
+                                  n2 = load_stage(cq + 5 * SO_C);
                     __stcs(orow, y.yr0);
                     __stcs(orow + op, y.yr1);
                     __stcs(orow + 2 * op, y.yi0);
@@ -229,13 +245,13 @@ __global__ void __launch_bounds__(SO_BLOCK, 8) so_rk4_kernel(SoArgs a) {
                             cp_async16(&sring[j][s][tid], srcbase + __double_as_longlong(ca[s * SO_C + 3]) * a.src_pitch);
                         asm volatile("cp.async.commit_group;" ::: "memory");
                     }
-                    const SoStage c0 = load_stage(cq), c1 = load_stage(cq + SO_C), c2 = load_stage(cq + 2 * SO_C);
                     if (c0.fotix < fo_ts) {               // see below
                         s0 = make_double2(nan, nan);
                         if (c1.fotix < fo_ts) s1 = s0;
                         if (c2.fotix < fo_ts) s2 = s0;
                     }
                     so_step(y, c0, c1, c2, k2, s0, s1, s2, h, hh, h6);
+                    c0 = n0; c1 = n1; c2 = n2;
                 }
                 next_out += SO_AHEAD;
                 continue;
