@@ -153,6 +153,11 @@ class CosmologicalModel(object):
         if getattr(self, "bgmodel", None) is not None:
             data["bg_tresult"] = self.bgmodel.tresult
             data["bg_yresult"] = self.bgmodel.yresult
+        if getattr(self, "source", None) is not None and not isinstance(self, SOCanonicalThreeStage):
+            # the reference keeps the second-order source term next to the first-order results
+            # (results.sourceterm, cosmomodels.py:1607-1612)
+            src = self.source
+            data["sourceterm"] = src.cpu().numpy() if hasattr(src, "cpu") else np.asarray(src)
         for name in ("potential_func", "nfields", "tend", "tstep_wanted", "simtstart", "cq"):
             if getattr(self, name, None) is not None:
                 data["param_" + name] = np.asarray(getattr(self, name))
@@ -817,6 +822,10 @@ def make_wrapper_model(modelfile, *args, **kwargs):
     z = np.load(modelfile, allow_pickle=False)
     classname = str(z["classname"]) if "classname" in z.files else "FOCanonicalTwoStage"
     cls = globals().get(classname, FOCanonicalTwoStage)
+    if issubclass(cls, SOCanonicalThreeStage):
+        # as in the reference, whose wrapper cannot build a second-order driver without its
+        # first-order stage: wrap the first-order file and run the driver again
+        raise ModelError("Results of %s cannot be wrapped: it needs its first order model." % classname)
     pot_params = {}
     if "pot_param_keys" in z.files:
         for key, val in zip(z["pot_param_keys"], z["pot_param_vals"]):
@@ -848,4 +857,7 @@ def make_wrapper_model(modelfile, *args, **kwargs):
                        potential_func=m.potential_func, pot_params=m.pot_params, nfields=m.nfields)
         bg.yresult, bg.tresult = z["bg_yresult"], z["bg_tresult"]
         m.bgmodel = bg
+        m.bgepsilon = bg.getepsilon()                       # cosmomodels.py:1661
+    # the source term of the second-order stage, when the file has one (:1607-1612)
+    m.source = z["sourceterm"] if "sourceterm" in z.files else None
     return m

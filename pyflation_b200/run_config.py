@@ -52,3 +52,11 @@ foclass = c.FOCanonicalTwoStage
 
 RESULTSDIR = os.path.join(os.getcwd(), "results")
 foresults = os.path.join(RESULTSDIR, "fo.npz")
+
+# second-order stage (run_config.py:178-181, 215-217, 258-260): the ramped class is the default
+soclass = c.CanonicalRampedSecondOrder
+soargs = {"solver": "rkdriver_tsix",
+          "nfields": 1,                 # only single field models can have second order calculated
+          "soclass": soclass}
+mrgresults = os.path.join(RESULTSDIR, "mrg.npz")
+soresults = os.path.join(RESULTSDIR, "so.npz")

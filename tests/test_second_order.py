@@ -132,6 +132,33 @@ def test_driver_setup_matches_reference_without_gpu():
         c.SOHorizonStart(m)
 
 
+def test_results_file_carries_the_source_term(tmp_path):
+    """The reference's second-order script wraps a first-order results file that carries the
+    source term (results.sourceterm -> model.source, bgepsilon recomputed; cosmomodels.py:1607-1661)
+    and hands it to SOCanonicalThreeStage: same round trip through the .npz counterpart."""
+    from pyflation_b200 import cosmomodels as c
+    g = load_so("so_msqphisq")
+    m = injected_first_order(g)
+    bg = c.CanonicalBackground(ystart=g["bgystart"].copy(), tend=83.0, tstep_wanted=0.01,
+                               potential_func=g["potential"], pot_params=dict(g["params"]), nfields=1)
+    bg.tresult, bg.yresult = m.tresult, np.nan_to_num(g["fo_bg0"])[:, :, None]
+    m.bgmodel = bg
+    path = m.saveallresults(filename=str(tmp_path / "fo.npz"))
+    w = c.make_wrapper_model(path)
+    assert np.array_equal(w.source, m.source) and w.bgepsilon.shape == (len(m.tresult),)
+    so = c.SOCanonicalThreeStage(w, soclass=c.CanonicalRampedSecondOrder)
+    assert np.array_equal(so.tstartindex, g["ramped_tstartindex"]) and so.source is w.source
+    del m.source
+    w2 = c.make_wrapper_model(m.saveallresults(filename=str(tmp_path / "fo_nosource.npz")))
+    assert w2.source is None
+    with pytest.raises(c.ModelError):
+        c.SOCanonicalThreeStage(w2)
+    so.yresult, so.tresult = g["ramped_yrows"], g["ramped_tresult"][g["ramped_rows"]]
+    sopath = so.saveallresults(filename=str(tmp_path / "so.npz"))
+    with pytest.raises(c.ModelError):
+        c.make_wrapper_model(sopath)
+
+
 def test_so_entry_points_reject_bad_arguments():
     from pyflation_b200 import _lib
     L = _lib.lib()
@@ -266,6 +293,31 @@ def test_second_order_launch_properties():
     err = col_err(got, want)
     print("1000-mode batch vs oracle on 4 columns: %.3e" % err)
     assert err < TOL
+
+
+@pytest.mark.gpu
+def test_second_order_script_runs_from_a_results_file(tmp_path, oracle):
+    """bin/pyflation_secondorder.py: wrap a first-order file that carries the source term, run
+    the three-stage driver with run_config.soargs (ramped class), save; compare with the golden."""
+    import importlib.util
+    from conftest import ROOT
+    from pyflation_b200 import cosmomodels as c
+    g = load_so("so_msqphisq")
+    m = c.FOCanonicalTwoStage(k=g["k"].copy(), potential_func=g["potential"], pot_params=dict(g["params"]),
+                              nfields=1, bgystart=g["bgystart"].copy(), cq=50, solver="rkdriver_tsix")
+    m.run(saveresults=False)
+    m.source = oracle.synthetic_source(m.tresult, m.k)
+    mrg = m.saveallresults(filename=str(tmp_path / "mrg.npz"))
+    spec = importlib.util.spec_from_file_location("pf_so_script", os.path.join(ROOT, "bin", "pyflation_secondorder.py"))
+    script = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(script)
+    out = script.runsomodel(mrg, filename=str(tmp_path / "results" / "so.npz"))
+    z = np.load(out)
+    assert str(z["classname"]) == "SOCanonicalThreeStage"
+    assert col_err(z["yresult"][g["ramped_rows"]], g["ramped_yrows"]) < TOL
+    assert np.array_equal(z["tresult"], g["ramped_tresult"])
+    with pytest.raises(c.ModelError):
+        script.runsomodel(mrg, soargs={"nfields": 2})
 
 
 @pytest.mark.gpu
