@@ -459,13 +459,21 @@ def measure_second_order(hbm_peak, reps=3, device_index=0):
         all_bytes = mode_steps * 32.0 + float(T) * nk * 32.0
         del out, prob, src
         torch.cuda.empty_cache()
+        traffic, traffic_src = None, None
+        try:                                               # profiler counters of this very launch
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r2c_so_v4_ncu_full.json")))
+            traffic = float(cap["dram_bytes_per_launch"])
+            traffic_src = "profiles/r2c_so_v4_ncu_full.json (ncu --set full capture of the same launch; static)"
+        except Exception:
+            pass
         return {"workload": name, "nk": nk, "T": T, "value": mode_steps / (ms * 1e-3), "ms": ms,
                 "unit": "k-mode second-order RK4-steps/s", "mode_kernel_ms": ms,
                 "output_policy": "full trajectory", "clocks": sampler.result(),
                 "roofline": {"bound": "hbm", "frac": alg_bytes / (ms * 1e-3) / 1e9 / hbm_peak, "timed": "mode kernel",
                              "hbm": {"achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                      "frac": alg_bytes / (ms * 1e-3) / 1e9 / hbm_peak,
-                                     "bytes_per_mode_step": 64,
+                                     "bytes_per_mode_step": 64, "algorithmic_bytes": alg_bytes,
+                                     "traffic": traffic, "traffic_source": traffic_src,
                                      "achieved_all_rows": all_bytes / (ms * 1e-3) / 1e9,
                                      "frac_all_rows": all_bytes / (ms * 1e-3) / 1e9 / hbm_peak}}}
     except Exception as err:
