@@ -269,6 +269,35 @@ class ShardedFirstOrder(object):
         return (asm.tensor() if asm.owner else None), asm
 
 
+def sharded_second_order(sharded, source, soclass=None, gather_every=None, **soclassargs):
+    """Second-order stage (SOCanonicalThreeStage, cosmomodels.py:1680-1790) on this rank's k-slab
+    of a finished sharded first-order run.  Modes never interact at second order either once the
+    source term is given, so the slabs stay where they are and nothing is communicated.
+
+    ``sharded``: a ShardedFirstOrder whose ``run()`` has completed.  ``source``: the source term of
+    the GLOBAL grid, (T_fo, nk) complex128, or a callable ``slice -> (T_fo, nk_r) array`` that
+    produces this rank's columns.  Returns the rank's driver after ``run()``; with
+    ``gather_every = s`` also rows 0, s, 2s, ... of the global (T_so, 4, nk) result, assembled on
+    every rank with one all-gather (``gather_rows``)."""
+    from . import cosmomodels
+    m = sharded.model
+    if m is None or m.yresult is None:
+        raise ValueError("run the sharded first-order stage first")
+    sl = my_slab(sharded.bounds, sharded.rank)
+    m.source = source(sl) if callable(source) else np.asarray(source)[:, sl]
+    so = cosmomodels.SOCanonicalThreeStage(m, soclass=soclass, **soclassargs)
+    so.run(saveresults=False)
+    if gather_every is None:
+        return so
+    rows = np.ascontiguousarray(so.yresult[::int(gather_every)])
+    local = torch.as_tensor(rows)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        if dist.get_backend() == "nccl":
+            local = local.to(torch.device("cuda", torch.cuda.current_device()))
+        return so, gather_rows(local, sharded.bounds)
+    return so, local
+
+
 def to_host(t):
     """Device tensor -> NumPy array through a page-locked staging tensor (torch's caching pinned
     allocator keeps repeated calls cheap; a pageable ``.cpu()`` of a 2^25-mode spectrum costs

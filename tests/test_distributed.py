@@ -36,6 +36,11 @@ def _worker(rank, world, port, out):
         ok_rows = np.array_equal(got, full)
         pr = torch.as_tensor(np.abs(full[:, 3, sl]) ** 2)
         ok_pr = np.array_equal(parallel.gather_spectrum(pr, bounds).numpy(), np.abs(full[:, 3, :]) ** 2)
+        # second-order rows are real (R, 4, nk): the same gather, float64 (parallel.sharded_second_order)
+        so_full = rng.standard_normal((3, 4, nk))
+        so_full[0, :, tsix > 40] = np.nan
+        got_so = parallel.gather_rows(torch.as_tensor(so_full[:, :, sl].copy()), bounds).numpy()
+        ok_rows = ok_rows and np.array_equal(got_so, so_full, equal_nan=True)
         # every rank derives the same boundaries without communicating
         blist = [None] * world
         dist.all_gather_object(blist, bounds.tolist())
