@@ -169,6 +169,36 @@ def test_helpers_default_grid():
     assert len(k) == 2053 and k[0] == 0.85e-60                 # BASELINE config 1 grid
 
 
+def test_helpers_utilities_behave_like_the_reference(tmp_path):
+    """The rest of pyflation/helpers.py (helpers.py:70-297), behaviour stated by its docstrings."""
+    import logging
+    from pyflation_b200 import helpers as h
+    assert h.eto10(1e-05) == r"1\times 10^{-5}" and h.eto10(2.5e+56) == r"2.5\times 10^{+56}"
+    assert h.klegend([1e-60]) == [r"$k=1\times 10^{-60}M_{\mathrm{PL}}$"]
+    assert h.klegend([1e-60], mpc=True)[0].endswith(r" M\mathrm{pc}$")
+    assert h.invmpc2mpl(2) == 2 * 2.625e-57 and h.mpl2invmpc() == 3.8095e+56
+    assert [h.ispower2(n) for n in (1, 2, 3, 1024, 1025, 0)] == [0, 1, 0, 10, 0, 0]
+    assert h.removedups([3, 1, 3, 2, 1]).tolist() == [3.0, 1.0, 2.0] and h.removedups([]).size == 0
+    f, kw = h.getintfunc(np.linspace(0, 1, 9))
+    assert f.__name__ == "romb" and abs(kw["dx"] - 0.125) < 1e-15
+    f, kw = h.getintfunc(np.linspace(0, 1, 10))
+    assert "simps" in f.__name__ and abs(f(kw["x"] ** 2, **kw) - 1 / 3.0) < 1e-3
+    with pytest.raises(ValueError):
+        h.getintfunc([])
+    assert list(h.cartesian_product([[1, 2], [3]])) == [[1, 3], [2, 3]]
+    assert h.cartesian(([1, 2, 3], [4, 5], [6, 7])).tolist()[:3] == [[1, 4, 6], [1, 4, 7], [1, 5, 6]]
+    assert h.cartesian(([1, 2], [4, 5])).shape == (4, 2)
+    assert h.find_nearest(np.array([1.0, 2.0, 4.0]), 2.9) == 2.0
+    target = tmp_path / "a" / "b" / "run.npz"
+    h.ensurepath(str(target))
+    assert os.path.isdir(str(tmp_path / "a" / "b"))
+    log = h.startlogging(logging.getLogger("pf_test_helpers"), str(tmp_path / "run.log"), logging.INFO)
+    log.info("hello")
+    for handler in list(log.handlers):
+        handler.flush(); handler.close(); log.removeHandler(handler)
+    assert "hello" in open(str(tmp_path / "run.log")).read()
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device the product path must fail loudly, not compute on the host."""
     import torch
