@@ -2,11 +2,11 @@
 B200-native implementation of its first-order path.
 
 ``from pyflation import cosmomodels`` (and ``rk4``, ``cmpotentials``, ``helpers``,
-``configuration``, ``run_config``, ``analysis`` with ``analysis.adiabatic`` /
+``configuration``, ``run_config``, ``sohelpers``, ``analysis`` with ``analysis.adiabatic`` /
 ``analysis.utilities``) gives the very module objects of :mod:`pyflation_b200`, so code written
 against the reference runs on the GPU path without editing its imports.  Modules of the
-reference outside the first-order path (``sourceterm``, ``solutions``, ``cosmographs``,
-``sohelpers``, ``analysis.nonadiabatic``) are out of scope and raise ImportError.
+reference outside the first- / second-order solver path (``sourceterm``, ``solutions``,
+``cosmographs``, ``analysis.nonadiabatic``) are out of scope and raise ImportError.
 """
 import importlib
 import sys
@@ -16,7 +16,7 @@ import pyflation_b200 as _impl
 __version__ = "0.2.3"                      # the reference version whose API is mirrored
 __b200_version__ = _impl.__version__
 
-for _name in ("configuration", "helpers", "cmpotentials", "rk4", "analysis", "cosmomodels", "run_config"):
+for _name in ("configuration", "helpers", "cmpotentials", "rk4", "analysis", "cosmomodels", "run_config", "sohelpers"):
     _mod = importlib.import_module("pyflation_b200." + _name)
     sys.modules[__name__ + "." + _name] = _mod
     globals()[_name] = _mod

@@ -159,6 +159,41 @@ def test_results_file_carries_the_source_term(tmp_path):
         c.make_wrapper_model(sopath)
 
 
+def test_combine_source_and_first_order_files(tmp_path):
+    """sohelpers.combine_source_and_fofile (sohelpers.py:20-86) on .npz files: the merged file is
+    what make_wrapper_model + SOCanonicalThreeStage expect (first-order data cut to the source's k
+    range, ``sourceterm`` added), with the reference's naming and checks."""
+    import pyflation_oracle as oracle
+    from pyflation import sohelpers, cosmomodels as c
+    g = load_so("so_msqphisq")
+    m = injected_first_order(g)
+    del m.source
+    bg = c.CanonicalBackground(ystart=g["bgystart"].copy(), tend=83.0, tstep_wanted=0.01,
+                               potential_func=g["potential"], pot_params=dict(g["params"]), nfields=1)
+    bg.tresult, bg.yresult = m.tresult, np.nan_to_num(g["fo_bg0"])[:, :, None]
+    m.bgmodel, m.foystart = bg, np.zeros((5, len(m.k)), dtype=complex)
+    fofile = m.saveallresults(filename=str(tmp_path / "fo.npz"))
+    nks = 3                                              # the source covers the first 3 modes
+    src = oracle.synthetic_source(m.tresult, m.k[:nks])
+    srcfile = str(tmp_path / "src-run1.npz")
+    np.savez(srcfile, sourceterm=src, k=m.k[:nks], nix=np.arange(len(m.tresult)))
+    merged = sohelpers.combine_source_and_fofile(srcfile, fofile)
+    assert os.path.basename(merged) == "foandsrc-run1.npz" and os.path.isfile(merged)
+    again = sohelpers.combine_source_and_fofile(srcfile, fofile)
+    assert os.path.basename(again) == "foandsrc_-run1.npz"
+    w = c.make_wrapper_model(merged)
+    assert w.yresult.shape[2] == nks and len(w.k) == nks and w.foystart.shape == (5, nks)
+    assert np.array_equal(w.source, src) and np.array_equal(w.fotstartindex, g["fotstartindex"][:nks])
+    so = c.SOCanonicalThreeStage(w)
+    assert np.array_equal(so.tstartindex, g["plain_tstartindex"][:nks])
+    np.savez(str(tmp_path / "src-short.npz"), sourceterm=src[:10], k=m.k[:nks], nix=np.arange(10))
+    with pytest.raises(ValueError):
+        sohelpers.combine_source_and_fofile(str(tmp_path / "src-short.npz"), fofile)
+    np.savez(str(tmp_path / "src-bad.npz"), k=m.k[:nks])
+    with pytest.raises(KeyError):
+        sohelpers.combine_source_and_fofile(str(tmp_path / "src-bad.npz"), fofile)
+
+
 def test_so_entry_points_reject_bad_arguments():
     from pyflation_b200 import _lib
     L = _lib.lib()
