@@ -34,6 +34,32 @@ __host__ __device__ constexpr int rec_of(int nf) {
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 
+// NumPy's float64 add-reduce over n <= 128 contiguous terms (DOUBLE_pairwise_sum): fewer than eight
+// terms are added in order; otherwise eight running sums take terms j, j+8, j+16, ..., are combined
+// as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), and the last n % 8 terms are added in order.  The sums
+// over fields of the reference -- np.sum in cmpotentials.py:837 (nflation's U) and
+// cosmomodels.py:569 (sum of phi'^2) -- round this way, and a last-bit difference in the background
+// is what the Bunch-Davies phase magnifies, so the device sums follow the same order.
+template <class F>
+__host__ __device__ __forceinline__ double np_sum(int n, F term) {
+    if (n < 8) {
+        double res = -0.0;
+        for (int i = 0; i < n; ++i) res += term(i);
+        return res;
+    }
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = term(j);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] += term(i + j);
+    }
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += term(i);
+    return res;
+}
+
 int check_model(const pf_model* m);
 
 // Flavour of the step records for (potential, nfields): PF_REC_DENSE (A, R, C[nf][nf]) or

@@ -38,13 +38,12 @@ __global__ void bunch_davies_kernel(int nf, int64_t nk, const double* __restrict
     const double ts = simtstart + (double)row * h;        // tresult[row], rk4.py:134
     const double astar = ainit * exp(ts);
     const double Hstar = y[2 * nf];
-    double eps = 0.0;
     for (int f = 0; f < nf; ++f) {
         ystart[(int64_t)(2 * f) * nk + i] = make_double2(y[2 * f], 0.0);
         ystart[(int64_t)(2 * f + 1) * nk + i] = make_double2(y[2 * f + 1], 0.0);
-        eps += y[2 * f + 1] * y[2 * f + 1];
     }
-    eps *= 0.5;
+    // epsilon = 0.5 * np.sum(phidots**2, axis=1) (cosmomodels.py:521), NumPy's summation order
+    const double eps = 0.5 * np_sum(nf, [&](int f) { return y[2 * f + 1] * y[2 * f + 1]; });
     ystart[(int64_t)(2 * nf) * nk + i] = make_double2(Hstar, 0.0);
     const double amp = 1.0 / (astar * sqrt(2.0 * kk));    // 1/(a sqrt(2k))
     double c = 1.0, s = 0.0;

@@ -115,14 +115,12 @@ __device__ __forceinline__ void potential(const double* __restrict__ p, const do
         if constexpr (D2) d2U[3] = -m2;
     } else if constexpr (POT == PF_NFLATION) {                // :791-846
         const double m2 = p[0] * p[0];
-        double acc = 0.0;
 #pragma unroll
         for (int i = 0; i < NF; ++i) {
-            acc += 0.5 * m2 * (phi[i] * phi[i]);
             dU[i] = m2 * phi[i];
             if constexpr (D2) d2U[i * NF + i] = m2;
         }
-        U = acc;
+        U = np_sum(NF, [&](int i) { return 0.5 * m2 * (phi[i] * phi[i]); });    // np.sum, :837
     } else if constexpr (POT == PF_QUARTICTWOFIELD) {         // :848-894
         const double a = p[0] * p[0], b = p[1] * p[1], l1 = p[2], l2 = p[3];
         const double f2 = phi[0] * phi[0], c2 = phi[1] * phi[1];

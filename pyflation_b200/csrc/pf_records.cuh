@@ -15,14 +15,13 @@ __device__ __forceinline__ void bg_rhs(const double* __restrict__ p, const doubl
     potential<POT, NF, false>(p, phi, U, dU, d2U);
     const double H = y[2 * NF];
     const double H2 = H * H;
-    double s = 0.0;
 #pragma unroll
     for (int i = 0; i < NF; ++i) {
         const double pd = y[2 * i + 1];
         dy[2 * i] = pd;                                   // cosmomodels.py:563
         dy[2 * i + 1] = -(U * pd + dU[i]) / H2;           // :566 (true division, as NumPy's real arrays)
-        s += pd * pd;
     }
+    const double s = np_sum(NF, [&](int i) { return y[2 * i + 1] * y[2 * i + 1]; });   // np.sum, :569
     dy[2 * NF] = -0.5 * s * H;                            // :569
 }
 

@@ -23,13 +23,8 @@ struct BgStateRt { double v[2 * RT + 1]; };
 // nflation: U = sum 1/2 m^2 phi_i^2, dU_i = m^2 phi_i, d2U = m^2 I      cmpotentials.py:830-843
 __device__ __forceinline__ void nflation_rt(double mass, int nf, const double* y, double& U, double* dU) {
     const double m2 = mass * mass;
-    double acc = 0.0;
-    for (int i = 0; i < nf; ++i) {
-        const double phi = y[2 * i];
-        acc += 0.5 * m2 * (phi * phi);
-        dU[i] = m2 * phi;
-    }
-    U = acc;
+    for (int i = 0; i < nf; ++i) dU[i] = m2 * y[2 * i];
+    U = np_sum(nf, [&](int i) { return 0.5 * m2 * (y[2 * i] * y[2 * i]); });   // np.sum, cmpotentials.py:837
 }
 
 __device__ __forceinline__ void bg_rhs_rt(double mass, int nf, const double* y, double* dy, double* dU) {
@@ -37,13 +32,12 @@ __device__ __forceinline__ void bg_rhs_rt(double mass, int nf, const double* y, 
     nflation_rt(mass, nf, y, U, dU);
     const double H = y[2 * nf];
     const double H2 = H * H;
-    double s = 0.0;
     for (int i = 0; i < nf; ++i) {
         const double pd = y[2 * i + 1];
         dy[2 * i] = pd;                                   // cosmomodels.py:563
         dy[2 * i + 1] = -(U * pd + dU[i]) / H2;           // :566
-        s += pd * pd;
     }
+    const double s = np_sum(nf, [&](int i) { return y[2 * i + 1] * y[2 * i + 1]; });
     dy[2 * nf] = -0.5 * s * H;                            // :569
 }
 
@@ -104,8 +98,7 @@ __global__ void stage_table_rt_kernel(double mass, int nf, double ainit, int64_t
     const double t = (s == 0) ? x : ((s == 3) ? x + h : x + h * 0.5);
     const double a = ainit * exp(t);                      // cosmomodels.py:637
     const double m2 = mass * mass;
-    double U = 0.0;
-    for (int i = 0; i < nf; ++i) U += 0.5 * m2 * (y[2 * i] * y[2 * i]);
+    const double U = np_sum(nf, [&](int i) { return 0.5 * m2 * (y[2 * i] * y[2 * i]); });
     const double H = y[2 * nf];
     const double invH2 = 1.0 / (H * H);
     o[0] = U * invH2;                                     // A
@@ -312,11 +305,10 @@ __global__ void derivs_rt_kernel(double mass, int nf, double ainit, int first_or
     if (c >= ncol) return;
     const int NB = 2 * nf + 1;
     const double m2 = mass * mass;
-    double U = 0.0;
-    for (int i = 0; i < nf; ++i) {
+    const double U = np_sum(nf, [&](int i) {
         const double phi = y[(int64_t)(2 * i) * ncol].re;                       // column 0
-        U += 0.5 * m2 * (phi * phi);
-    }
+        return 0.5 * m2 * (phi * phi);
+    });
     const cx H = y[(int64_t)(2 * nf) * ncol + c];
     const cx invH2 = cxinv(cxmul(H, H));
     cx s = {0.0, 0.0};

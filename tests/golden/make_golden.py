@@ -38,6 +38,15 @@ def subsample(nk_full, n):
     return np.unique(np.linspace(0, nk_full - 1, n).round().astype(np.int64))
 
 
+def _unequal(nf):
+    """nflation start vector with a different value in every field (total amplitude ~ 17)."""
+    y = []
+    for i in range(nf):
+        y += [18.0 / np.sqrt(nf) * (0.8 + 0.2 * i / (nf - 1) + 0.013 * ((i * 5) % 7)),
+              -0.1 / np.sqrt(nf) * (1.0 + 0.11 * ((i * 3) % 5))]
+    return y + [0.0]
+
+
 # name -> (potential, nfields, pot_params, bgystart, full-grid size or "K4", #modes kept,
 #          row stride, driver class name, extra kwargs)
 FIXTURES = {
@@ -81,6 +90,12 @@ FIXTURES = {
     "nflation13": ("nflation", 13, {"nfields": 13}, None, 2 ** 10, 2, 100,
                    "FOCanonicalTwoStage", {}),
     "nflation16": ("nflation", 16, {"nfields": 16}, None, 2 ** 10, 2, 100,
+                   "FOCanonicalTwoStage", {}),
+    # unequal fields: the sums over fields (np.sum in cmpotentials.py:837, cosmomodels.py:569) are
+    # then sensitive to NumPy's pairwise summation order (8 fields: the tree; 9: tree + remainder)
+    "nflation8u": ("nflation", 8, {"nfields": 8}, _unequal(8), 2 ** 10, 2, 100,
+                   "FOCanonicalTwoStage", {}),
+    "nflation9u": ("nflation", 9, {"nfields": 9}, _unequal(9), 2 ** 10, 2, 100,
                    "FOCanonicalTwoStage", {}),
     "hybridquartic": ("hybridquartic", 2, {"nfields": 2}, [1e-2, 2e-8, 1.63e-9, 3.26e-7, 0],
                       2 ** 10, 5, 50, "FOCanonicalTwoStage", {}),
