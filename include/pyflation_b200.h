@@ -260,14 +260,17 @@ int pf_scatter_slab(int64_t nrows_times_nvar, int64_t nk_r, int64_t nk, int64_t 
  *     a stage whose fotix lies before a mode's first-order start reads NaN there in the reference
  *     and poisons the mode; ystart_dev [4][nk].
  *   ramp_host (may be NULL) = {a, b, c, d, e}: S is multiplied by (tanh(a (t - tstart_k - b)) + c)/d
- *     while |t - tstart_k - b| < e, and by 0 at the stage with t/h == tsix_k (:925-944);
+ *     while |t - tstart_k - b| < e, and by 0 at the stage with t/h == the model's tstartindex_k
+ *     (:925-944): ramp_tsix_dev[nk], NULL = tsix_dev (they differ only when the solver is called
+ *     with other start rows than the model's, e.g. rk4stepks);
  *     tstart_dev[nk] = first-order start times (required with a ramp).
  *   state_dev [4][nk], yout_dev [rows][4][out_pitch or nk] float64, out_every: as pf_fo_run. */
 #define PF_SO_COEF 6
 int pf_so_run(int64_t nk, const double *k_dev, const int64_t *tsix_dev, const int64_t *fo_tsix_dev,
               const double *ystart_dev, const double *coef_dev, const double *source_dev,
               int64_t source_rows, int64_t source_pitch, const double *tstart_dev,
-              const double *ramp_host, int64_t T, double h, int64_t t0, int64_t t1,
+              const int64_t *ramp_tsix_dev, const double *ramp_host, int64_t T, double h,
+              int64_t t0, int64_t t1,
               double *state_dev, double *yout_dev, int64_t out_every, int64_t out_pitch,
               void *stream);
 /* One right-hand side dydx_dev[4][nk] = derivs(y_dev[4][nk], t): coef_dev[PF_SO_COEF] of that

@@ -107,7 +107,7 @@ def lib():
     L.pf_bunch_davies.argtypes = [c_int, c_i64, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_dbl, c_dbl, c_int,
                                   c_int, c_vp, c_vp]
     L.pf_derivs.argtypes = [mp, c_int, c_i64, c_vp, c_dbl, c_vp, c_vp, c_vp]
-    L.pf_so_run.argtypes = [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp,
+    L.pf_so_run.argtypes = [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp,
                             ctypes.POINTER(c_dbl), c_i64, c_dbl, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp]
     L.pf_so_derivs.argtypes = [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(c_dbl),
                                c_vp, c_vp]

@@ -36,6 +36,7 @@ struct SoArgs {
     int64_t nk;
     const double* __restrict__ k;
     const int64_t* __restrict__ tsix;      // second-order start rows
+    const int64_t* __restrict__ rtsix;     // rows the ramp compares t/h with (the model's tstartindex)
     const int64_t* __restrict__ fo_tsix;   // first-order start rows (null: never poison)
     const double* __restrict__ ystart;     // [4][nk]
     const double* __restrict__ coef;       // [T][3][SO_C]
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(SO_BLOCK, PF_SO_MINB) so_rk4_kernel(SoArgs a) 
     const int64_t ts = a.tsix[kk];
     const double k2 = a.k[kk] * a.k[kk];
     const double tstart = a.tstart ? a.tstart[kk] : 0.0;
-    const double tsd = (double)ts;
+    const double tsd = (double)(a.rtsix ? a.rtsix[kk] : ts);
     const int64_t fo_ts = a.fo_tsix ? a.fo_tsix[kk] : INT64_MIN;
     const double h = a.h, hh = h * 0.5, h6 = h / 6.0;     // rk4.py:31-32
     const double nan = qnan();
@@ -323,7 +324,7 @@ __global__ void so_derivs_kernel(SoArgs a, const double* __restrict__ y, const d
     const double k2 = a.k[kk] * a.k[kk];
     double2 s = srcrow ? reinterpret_cast<const double2*>(srcrow)[kk] : make_double2(0.0, 0.0);
     if (a.ramp) {
-        const double r = ramp_factor(a.coef, a.tstart[kk], (double)a.tsix[kk], a.ra, a.rb, a.rc, a.rd, a.re);
+        const double r = ramp_factor(a.coef, a.tstart[kk], (double)a.rtsix[kk], a.ra, a.rb, a.rc, a.rd, a.re);
         if (r != 1.0) { s.x = r * s.x; s.y = r * s.y; }
     }
     if (a.fo_tsix && c.fotix < a.fo_tsix[kk]) s = make_double2(qnan(), qnan());
@@ -351,7 +352,8 @@ using namespace pf;
 extern "C" int pf_so_run(int64_t nk, const double* k_dev, const int64_t* tsix_dev, const int64_t* fo_tsix_dev,
                          const double* ystart_dev, const double* coef_dev, const double* source_dev,
                          int64_t source_rows, int64_t source_pitch, const double* tstart_dev,
-                         const double* ramp_host, int64_t T, double h, int64_t t0, int64_t t1,
+                         const int64_t* ramp_tsix_dev, const double* ramp_host, int64_t T, double h,
+                         int64_t t0, int64_t t1,
                          double* state_dev, double* yout_dev, int64_t out_every, int64_t out_pitch,
                          void* stream) {
     if (nk < 0 || T < 1 || t0 < 0 || t1 > T || t0 > t1 || out_every < 0) {
@@ -372,6 +374,7 @@ extern "C" int pf_so_run(int64_t nk, const double* k_dev, const int64_t* tsix_de
     if (out_pitch != 0 && out_pitch < nk) { set_error("pf_so_run: out_pitch=%lld is smaller than nk=%lld", (long long)out_pitch, (long long)nk); return PF_E_ARG; }
     SoArgs a;
     a.nk = nk; a.k = k_dev; a.tsix = tsix_dev; a.fo_tsix = fo_tsix_dev; a.ystart = ystart_dev;
+    a.rtsix = ramp_tsix_dev ? ramp_tsix_dev : tsix_dev;
     a.coef = coef_dev; a.src = source_dev; a.src_pitch = source_pitch;
     int rc = fill_ramp(a, ramp_host, tstart_dev, "pf_so_run");
     if (rc) return rc;
@@ -391,7 +394,7 @@ extern "C" int pf_so_derivs(int64_t nk, const double* k_dev, const int64_t* tsix
     if (nk == 0) return PF_OK;
     if (!k_dev || !y_dev || !coef_dev || !dydx_dev) { set_error("pf_so_derivs: null buffer"); return PF_E_ARG; }
     SoArgs a{};
-    a.nk = nk; a.k = k_dev; a.tsix = tsix_dev; a.fo_tsix = fo_tsix_dev; a.coef = coef_dev;
+    a.nk = nk; a.k = k_dev; a.tsix = tsix_dev; a.rtsix = tsix_dev; a.fo_tsix = fo_tsix_dev; a.coef = coef_dev;
     int rc = fill_ramp(a, ramp_host, tstart_dev, "pf_so_derivs");
     if (rc) return rc;
     if (a.ramp && !tsix_dev) { set_error("pf_so_derivs: a ramp needs tsix_dev"); return PF_E_ARG; }

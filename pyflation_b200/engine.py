@@ -644,7 +644,7 @@ class SecondOrderProblem(object):
     rkdriver_tsix, cosmomodels.py:1755-1790)."""
 
     def __init__(self, model, k, tsix, ystart, simtstart, T, h, fo_bg0, bgepsilon, fo_simtstart,
-                 fo_tstep, fo_tsix=None, source=None, ramp=None, tstart=None, device=None):
+                 fo_tstep, fo_tsix=None, source=None, ramp=None, tstart=None, ramp_tsix=None, device=None):
         self.dev = require_cuda(device)
         self.model, self.T, self.h, self.simtstart = model, int(T), float(h), float(simtstart)
         k = np.ascontiguousarray(np.atleast_1d(k), dtype=np.float64)
@@ -663,11 +663,13 @@ class SecondOrderProblem(object):
             up = lambda a: torch.as_tensor(a).to(self.dev)
             self.k, self.tsix, self.ystart, self.coef = up(k), up(tsix), up(ystart), up(coef)
             self.fo_tsix = None if fo_tsix is None else up(np.ascontiguousarray(fo_tsix, dtype=np.int64))
-            self.tstart = None
+            self.tstart = self.ramp_tsix = None
             if ramp is not None:
                 if tstart is None:
                     raise ValueError("a ramped source needs the first-order start times")
                 self.tstart = up(np.ascontiguousarray(np.broadcast_to(np.asarray(tstart, dtype=np.float64), (nk,))))
+                if ramp_tsix is not None:              # the model's start rows, when the solver's differ
+                    self.ramp_tsix = up(np.ascontiguousarray(np.broadcast_to(np.asarray(ramp_tsix, dtype=np.int64), (nk,))))
             self.source = None
             if source is not None:
                 if torch.is_tensor(source):
@@ -691,7 +693,8 @@ class SecondOrderProblem(object):
             _lib.check(L.pf_so_run(self.nk, _ptr(self.k), _ptr(self.tsix), _ptr(self.fo_tsix),
                                    _ptr(self.ystart), _ptr(self.coef), _ptr(src),
                                    0 if src is None else src.shape[0], 0 if src is None else src.shape[1],
-                                   _ptr(self.tstart), self._ramp_ptr, self.T, self.h, int(t0), int(t1),
+                                   _ptr(self.tstart), _ptr(self.ramp_tsix), self._ramp_ptr, self.T, self.h,
+                                   int(t0), int(t1),
                                    _ptr(self.state), _ptr(yout), int(out_every), int(out_pitch),
                                    _stream_ptr(stream)))
 

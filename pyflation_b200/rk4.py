@@ -219,7 +219,8 @@ def _run_second_order(model, ystart, simtstart, tsix, T, h):
     pm = engine.make_model(model.potential_func, model.pot_params, model.nfields, model.ainit)
     ramp = model.rampargs if model.ramped else None
     prob = engine.SecondOrderProblem(pm, k, tsix, ystart, simtstart, T, h, source=model.source,
-                                     ramp=ramp, tstart=model.tstart if model.ramped else None, **inp)
+                                     ramp=ramp, tstart=model.tstart if model.ramped else None,
+                                     ramp_tsix=model.tstartindex if model.ramped else None, **inp)
     yarr = engine.second_order_host(prob)
     last_transfer.update(h2d_bytes=prob.h2d_bytes, d2h_bytes=prob.d2h_bytes)
     return yarr

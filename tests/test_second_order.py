@@ -203,7 +203,7 @@ def test_so_entry_points_reject_bad_arguments():
     def run(nk=4, T=10, h=0.02, t0=0, t1=10, src=nul, rows=0, pitch=0, tstart=nul, ramp=None,
             state=nul, yout=one, every=1, opitch=0, k=one):
         r = None if ramp is None else (ctypes.c_double * 5)(*ramp)
-        return L.pf_so_run(nk, k, one, nul, one, one, src, rows, pitch, tstart,
+        return L.pf_so_run(nk, k, one, nul, one, one, src, rows, pitch, tstart, nul,
                            None if r is None else ctypes.cast(r, ctypes.POINTER(ctypes.c_double)),
                            T, h, t0, t1, state, yout, every, opitch, nul)
     assert run(nk=-1) == -1
@@ -254,6 +254,35 @@ def test_second_order_stage_matches_reference_golden(name):
     assert col_err(d, g["homog_dydx"]) < 1e-12
     with pytest.raises(c.ModelError):
         hm.derivs(g["homog_y"], float(g["homog_t"]))
+
+
+@pytest.mark.gpu
+def test_single_step_and_column_subsets(oracle):
+    """rk4.rk4stepks on a second-order model (a two-row solve on the device) against the oracle's
+    RK4 step, and derivs for a subset of the columns (``k`` / ``kix`` keywords)."""
+    from pyflation_b200 import cosmomodels as c, rk4
+    g = load_so("so_lambdaphi4")
+    m = injected_first_order(g)
+    so = c.SOCanonicalThreeStage(m, soclass=c.CanonicalRampedSecondOrder)
+    so.setup_soclass()
+    sm = so.somodel
+    f = oracle.make_so_rhs(g["potential"], g["params"], g["k"], g["ainit"], m.yresult, float(g["fo_simtstart"]),
+                           float(g["fo_tstep"]), g["bgepsilon"], m.source, ramp=g["ramp"], tstart=g["fotstart"],
+                           tstartindex=so.tstartindex, so_tstep=so.tstep_wanted)
+    rng = np.random.RandomState(3)
+    # the middle row is a mode's own start row: the ramp is zero there for that mode (:935-937), which
+    # the two-row solve must take from the MODEL's start rows, not from the solver's (all zero)
+    for row in (int(so.tstartindex.max()) + 7, int(so.tstartindex[1]), int(so.tstartindex.max()) + 400):
+        x = so.simtstart + row * so.tstep_wanted
+        y = rng.normal(size=(4, len(g["k"]))) * 1e-3
+        want = oracle.rk4_step(x, y, so.tstep_wanted, f(y, x), f)
+        got = rk4.rk4stepks(x, y, so.tstep_wanted, None, {}, sm.derivs)
+        assert col_err(got[None], want[None]) < 1e-12
+        kix = np.array([0, 2])
+        sub = sm.derivs(y[:, kix], x + 0.5 * so.tstep_wanted, k=g["k"][kix], kix=kix)
+        assert col_err(sub[None], f(y, x + 0.5 * so.tstep_wanted)[:, kix][None]) < 1e-12
+    with pytest.raises(c.ModelError):
+        sm.derivs(y, x, k=g["k"], kix=None)
 
 
 @pytest.mark.gpu
