@@ -632,6 +632,17 @@ def so_stage_coefficients(model, t, fo_bg0, bgepsilon, fo_simtstart, fo_tstep, s
     return coef
 
 
+def _upload(a, dev):
+    """Host array -> device tensor.  Read-only arrays (e.g. straight out of an .npz file) are
+    uploaded as they are: the copy to the device never writes to them."""
+    import warnings
+    if a is None:
+        return None
+    with warnings.catch_warnings():
+        warnings.filterwarnings("ignore", message="The given NumPy array is not writable")
+        return torch.as_tensor(np.ascontiguousarray(a)).to(dev)
+
+
 def _ramp_array(ramp):
     if ramp is None:
         return None, None
@@ -660,7 +671,7 @@ class SecondOrderProblem(object):
         coef = so_stage_coefficients(model, t, fo_bg0, bgepsilon, fo_simtstart, fo_tstep, self.h, self.dev)
         self.h2d_bytes = 0
         with torch.cuda.device(self.dev):
-            up = lambda a: torch.as_tensor(a).to(self.dev)
+            up = lambda a: _upload(a, self.dev)
             self.k, self.tsix, self.ystart, self.coef = up(k), up(tsix), up(ystart), up(coef)
             self.fo_tsix = None if fo_tsix is None else up(np.ascontiguousarray(fo_tsix, dtype=np.int64))
             self.tstart = self.ramp_tsix = None
@@ -743,7 +754,7 @@ def so_derivs_device(model, y, t, k, fo_bg0, bgepsilon, fo_simtstart, fo_tstep, 
         coef[4], coef[5] = t, t / so_tstep
     keep, rptr = _ramp_array(ramp)
     with torch.cuda.device(dev):
-        up = lambda a: None if a is None else torch.as_tensor(np.ascontiguousarray(a)).to(dev)
+        up = lambda a: _upload(a, dev)
         kd, yd, cd = up(k), up(y), up(coef)
         sd = up(None if source_row is None else np.asarray(source_row, dtype=np.complex128))
         td = up(None if tstart is None else np.broadcast_to(np.asarray(tstart, dtype=np.float64), (nk,)))
