@@ -18,11 +18,24 @@ pytestmark = pytest.mark.gpu
 
 
 def _torchrun(world, port, *extra):
+    # the worker processes share the GPU(s) with this pytest process, whose caching allocator may
+    # still hold most of the device memory from earlier tests (full trajectories of 40-100 GB)
+    import gc
+    import torch
+    gc.collect()
+    torch.cuda.empty_cache()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "multigpu_worker.py")] + list(extra)
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
-    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    if res.returncode != 0:                              # keep the whole log where gpurun brings it back
+        try:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", "multigpu_worker_failure.log"), "w") as fh:
+                fh.write(res.stdout + "\n==== stderr ====\n" + res.stderr)
+        except OSError:
+            pass
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-12000:]
     assert "OK" in res.stdout
     return res.stdout
 
