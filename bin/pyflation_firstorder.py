@@ -13,51 +13,41 @@ import os
 import sys
 
 try:
-    from pyflation_b200 import run_config, helpers, cosmomodels as c
+    from pyflation_b200 import cli, run_config, helpers, cosmomodels as c
 except ImportError:
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-    from pyflation_b200 import run_config, helpers, cosmomodels as c
+    from pyflation_b200 import cli, run_config, helpers, cosmomodels as c
 
 log = logging.getLogger("pyflation_firstorder")
 
 
 def runfomodel(filename=None, foargs=None, foclass=None, row_stride=1):
-    """Create the first-order driver with ``foargs``, run it and save the results."""
-    if foargs is None:
-        foargs = dict(run_config.foargs)
-    if "k" not in foargs:
-        foargs["k"] = helpers.seq(run_config.kinit, run_config.kend, run_config.deltak)
-    if filename is None:
-        filename = run_config.foresults
-    if not foclass:
-        foclass = run_config.foclass
-    if not issubclass(foclass, c.FOCanonicalTwoStage):
+    """Build the first-order driver from ``foargs`` (default: run_config.foargs, k grid from
+    run_config's range), run it on the GPU and save the results; returns the file written."""
+    settings = dict(run_config.foargs if foargs is None else foargs)
+    settings.setdefault("k", helpers.seq(run_config.kinit, run_config.kend, run_config.deltak))
+    driver_class = foclass or run_config.foclass
+    if not issubclass(driver_class, c.FOCanonicalTwoStage):
         raise ValueError("Must use FOCanonicalTwoStage class for first order run!")
-    model = foclass(**foargs)
+    target = filename or run_config.foresults
+    model = driver_class(**settings)
     if row_stride != 1:
         model.row_stride = row_stride
     try:
-        log.debug("Starting model run...")
         model.run(saveresults=False)
-        log.debug("Model run finished.")
     except c.ModelError:
         log.exception("Something went wrong with model, quitting!")
         sys.exit(1)
     try:
-        dirname = os.path.dirname(filename)
-        if dirname and not os.path.isdir(dirname):
-            os.makedirs(dirname)
-        filename = model.saveallresults(filename=filename)
-        log.info("Successfully ran and saved simulation in file %s.", filename)
+        cli.make_parent_directory(target)
+        target = model.saveallresults(filename=target)
+        log.info("Successfully ran and saved simulation in file %s.", target)
     except Exception:
         log.exception("IO error, nothing saved!")
-    del model
-    return filename
+    return target
 
 
 def main(argv=None):
-    if not argv:
-        argv = sys.argv
     parser = optparse.OptionParser()
     parser.add_option("-f", "--filename", action="store", dest="foresults", default=run_config.foresults,
                       type="string", metavar="FILE", help="file to store results")
@@ -67,31 +57,19 @@ def main(argv=None):
                       help="keep every N-th k of the configured range")
     parser.add_option("--rowstride", action="store", dest="rowstride", default=1, type="int",
                       help="keep every N-th time row of the trajectory")
-    loggroup = optparse.OptionGroup(parser, "Log Options", "These options affect the verbosity of the log output.")
-    loggroup.add_option("-q", "--quiet", action="store_const", const=logging.FATAL, dest="loglevel",
-                        help="only print fatal error messages")
-    loggroup.add_option("-v", "--verbose", action="store_const", const=logging.INFO, dest="loglevel",
-                        help="print informative messages")
-    loggroup.add_option("--debug", action="store_const", const=logging.DEBUG, dest="loglevel",
-                        help="log lots of debugging information", default=run_config.LOGLEVEL)
-    loggroup.add_option("--console", action="store_true", dest="console", default=False,
-                        help="if selected matches console log level to selected log level")
-    parser.add_option_group(loggroup)
-    options, _ = parser.parse_args(args=argv[1:])
-    logging.basicConfig(level=options.loglevel if options.console else logging.WARN)
+    cli.add_log_options(parser, run_config.LOGLEVEL)
+    options, _ = parser.parse_args(args=(argv or sys.argv)[1:])
+    cli.configure_logging(options)
     log.info("-----------First order run requested------------------")
     if os.path.isfile(options.foresults):
         raise IOError("First order results file already exists!")
-    if options.fixture != "":
-        try:
-            foargs = dict(run_config.fixtures[options.fixture])
-            log.info("Potential %s selected." % foargs["potential_func"])
-        except KeyError:
-            log.exception("Fixture doesn't exist in run_config.py!")
-            return 1
-    else:
-        foargs = dict(run_config.foargs)
-    foargs["k"] = helpers.seq(run_config.kinit, run_config.kend, run_config.deltak)[::max(1, options.kstride)]
+    if options.fixture and options.fixture not in run_config.fixtures:
+        log.error("Fixture doesn't exist in run_config.py!")
+        return 1
+    foargs = dict(run_config.fixtures[options.fixture] if options.fixture else run_config.foargs)
+    log.info("Potential %s selected." % foargs["potential_func"])
+    kgrid = helpers.seq(run_config.kinit, run_config.kend, run_config.deltak)
+    foargs["k"] = kgrid[::max(1, options.kstride)]
     try:
         runfomodel(filename=options.foresults, foargs=foargs, row_stride=options.rowstride)
     except Exception:
