@@ -457,7 +457,42 @@ def measure_second_order(hbm_peak, reps=3, device_index=0):
         mode_steps = float(np.sum(T - 1 - tsix))
         alg_bytes = mode_steps * 64.0
         all_bytes = mode_steps * 32.0 + float(T) * nk * 32.0
-        del out, prob, src
+        del out, prob
+        # end to end through the host path: source term in page-locked host memory in, trajectory in
+        # page-locked host memory out, both streamed through time windows (engine.second_order_host)
+        e2e = None
+        try:
+            src_host = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+            src_host.copy_(src)
+            del src
+            torch.cuda.empty_cache()
+            eprob = engine.SecondOrderProblem(pm, k, tsix, np.zeros((4, nk)), 0.0, T, h2,
+                                              fo_bg0=m.bgmodel.yresult[:T_fo, :, 0], bgepsilon=m.bgepsilon,
+                                              fo_simtstart=0.0, fo_tstep=H, fo_tsix=m.fotstartindex,
+                                              source=src_host, ramp=ramp, tstart=m.fotstart)
+            host_out = torch.empty((T, 4, nk), dtype=torch.float64, pin_memory=True)
+            engine.second_order_host(eprob, out=host_out)
+            walls = []
+            for _ in range(reps):
+                eprob.h2d_bytes = 0
+                torch.cuda.synchronize()
+                t_start = time.perf_counter()
+                engine.second_order_host(eprob, out=host_out)
+                walls.append(time.perf_counter() - t_start)
+            assert bool(torch.isfinite(host_out[T - 1]).all())
+            wall = float(np.mean(walls))
+            e2e = {"value": mode_steps / wall, "unit": "k-mode second-order RK4-steps/s", "ms_per_step": wall * 1e3,
+                   "h2d_bytes_per_step": int(eprob.h2d_bytes), "d2h_bytes_per_step": int(eprob.d2h_bytes),
+                   "pcie_GBs_each_way": [eprob.h2d_bytes / wall / 1e9, eprob.d2h_bytes / wall / 1e9],
+                   "api": "engine.second_order_host(problem with a host-resident source, out=<pinned buffer>): "
+                          "source rows in and result rows out streamed through time windows"}
+            del eprob, host_out, src_host
+        except Exception as err:
+            e2e = {"error": repr(err)}
+        try:                                               # give the 16 GB of pinned memory back
+            torch._C._host_emptyCache()
+        except Exception:
+            pass
         torch.cuda.empty_cache()
         traffic, traffic_src = None, None
         try:                                               # profiler counters of this very launch
@@ -467,7 +502,7 @@ def measure_second_order(hbm_peak, reps=3, device_index=0):
         except Exception:
             pass
         return {"workload": name, "nk": nk, "T": T, "value": mode_steps / (ms * 1e-3), "ms": ms,
-                "unit": "k-mode second-order RK4-steps/s", "mode_kernel_ms": ms,
+                "unit": "k-mode second-order RK4-steps/s", "mode_kernel_ms": ms, "e2e": e2e,
                 "output_policy": "full trajectory", "clocks": sampler.result(),
                 "roofline": {"bound": "hbm", "frac": alg_bytes / (ms * 1e-3) / 1e9 / hbm_peak, "timed": "mode kernel",
                              "hbm": {"achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

@@ -655,7 +655,8 @@ class SecondOrderProblem(object):
     rkdriver_tsix, cosmomodels.py:1755-1790)."""
 
     def __init__(self, model, k, tsix, ystart, simtstart, T, h, fo_bg0, bgepsilon, fo_simtstart,
-                 fo_tstep, fo_tsix=None, source=None, ramp=None, tstart=None, ramp_tsix=None, device=None):
+                 fo_tstep, fo_tsix=None, source=None, ramp=None, tstart=None, ramp_tsix=None, device=None,
+                 stream_source_bytes=64 << 20):
         self.dev = require_cuda(device)
         self.model, self.T, self.h, self.simtstart = model, int(T), float(h), float(simtstart)
         k = np.ascontiguousarray(np.atleast_1d(k), dtype=np.float64)
@@ -681,33 +682,63 @@ class SecondOrderProblem(object):
                 self.tstart = up(np.ascontiguousarray(np.broadcast_to(np.asarray(tstart, dtype=np.float64), (nk,))))
                 if ramp_tsix is not None:              # the model's start rows, when the solver's differ
                     self.ramp_tsix = up(np.ascontiguousarray(np.broadcast_to(np.asarray(ramp_tsix, dtype=np.int64), (nk,))))
-            self.source = None
+            # the source term: resident on the device when it is given there or is small; a large
+            # host array stays on the host and second_order_host streams it through time windows
+            self.source = self.source_host = None
+            self.fotix_host = np.ascontiguousarray(coef[..., 3]).view(np.int64)
             if source is not None:
-                if torch.is_tensor(source):
-                    src = source.to(self.dev)
-                else:
-                    src = np.asarray(source)
-                    self.h2d_bytes += src.shape[0] * nk * 16
-                    src = up(np.ascontiguousarray(src, dtype=np.complex128))
+                host = source if (torch.is_tensor(source) and source.device.type == "cpu") else None
+                if not torch.is_tensor(source):
+                    import warnings
+                    with warnings.catch_warnings():       # a read-only array (np.load) is only read
+                        warnings.filterwarnings("ignore", message="The given NumPy array is not writable")
+                        host = torch.from_numpy(np.ascontiguousarray(np.asarray(source), dtype=np.complex128))
+                src = host if host is not None else source
                 if src.dtype != torch.complex128 or src.dim() != 2 or src.shape[1] != nk:
                     raise ValueError("source must be complex128 of shape (T_fo, len(k))")
-                if int(coef[: max(self.T - 1, 1), :, 3].view(np.int64).max()) >= src.shape[0]:
+                if int(self.fotix_host[: max(self.T - 1, 1)].max()) >= src.shape[0]:
                     raise IndexError("second-order stage time outside the source term")
-                self.source = src.contiguous()
+                if host is not None and host.numel() * 16 >= stream_source_bytes:
+                    self.source_host = host.contiguous()
+                else:
+                    if host is not None:
+                        self.h2d_bytes += host.numel() * 16
+                    self.source = src.to(self.dev).contiguous()
             self.state = torch.zeros((4, nk), dtype=torch.float64, device=self.dev)
         self._ramp_keep, self._ramp_ptr = _ramp_array(ramp)
 
-    def launch(self, t0, t1, yout, out_every=1, stream=None, out_pitch=0):
+    def launch(self, t0, t1, yout, out_every=1, stream=None, out_pitch=0, source_window=None):
+        """K9 over rows [t0, t1).  ``source_window`` = (device tensor holding source rows
+        [r0, r0 + n), r0): the streamed form of a host-resident source term."""
         L = _lib.lib()
-        src = self.source
+        if source_window is not None:
+            slab, r0 = source_window
+            # the kernel indexes source_dev[fotix * pitch + k]: offset the base so that row r0 is slab[0]
+            src_ptr, src_rows, pitch = slab.data_ptr() - int(r0) * self.nk * 16, int(r0) + slab.shape[0], self.nk
+        elif self.source is not None:
+            src_ptr, src_rows, pitch = self.source.data_ptr(), self.source.shape[0], self.source.shape[1]
+        elif self.source_host is not None:                # not streamed: make it resident once
+            with torch.cuda.device(self.dev):
+                self.source = self.source_host.to(self.dev)
+            self.h2d_bytes += self.source_host.numel() * 16
+            self.source_host = None
+            src_ptr, src_rows, pitch = self.source.data_ptr(), self.source.shape[0], self.source.shape[1]
+        else:
+            src_ptr, src_rows, pitch = 0, 0, 0
         with torch.cuda.device(self.dev):
             _lib.check(L.pf_so_run(self.nk, _ptr(self.k), _ptr(self.tsix), _ptr(self.fo_tsix),
-                                   _ptr(self.ystart), _ptr(self.coef), _ptr(src),
-                                   0 if src is None else src.shape[0], 0 if src is None else src.shape[1],
+                                   _ptr(self.ystart), _ptr(self.coef), ctypes.c_void_p(src_ptr), src_rows, pitch,
                                    _ptr(self.tstart), _ptr(self.ramp_tsix), self._ramp_ptr, self.T, self.h,
-                                   int(t0), int(t1),
-                                   _ptr(self.state), _ptr(yout), int(out_every), int(out_pitch),
-                                   _stream_ptr(stream)))
+                                   int(t0), int(t1), _ptr(self.state), _ptr(yout), int(out_every),
+                                   int(out_pitch), _stream_ptr(stream)))
+
+    def source_rows(self, t0, t1):
+        """[r0, r1): rows of the source term that the steps of result rows [t0, t1) read."""
+        last = min(t1, self.T - 1)
+        if last <= t0:
+            return 0, 0
+        f = self.fotix_host[t0:last]
+        return int(f.min()), int(f.max()) + 1
 
 
 def second_order_device(prob, out=None, out_every=1):
@@ -719,20 +750,114 @@ def second_order_device(prob, out=None, out_every=1):
     return out
 
 
-def second_order_host(prob, slab_bytes=4 << 30):
-    """The whole (T, 4, nk) float64 trajectory in host memory; results larger than ``slab_bytes``
-    go through time windows (state carried on the device between them)."""
+def _threaded_copy(dst, src, pool, parts=4):
+    """dst[...] = src for large host arrays, split over a few threads (NumPy releases the GIL)."""
+    n = src.shape[0]
+    if pool is None or n < 2 * parts:
+        np.copyto(dst, src)
+        return
+    edges = [(n * i) // parts for i in range(parts + 1)]
+    list(pool.map(lambda i: np.copyto(dst[edges[i]:edges[i + 1]], src[edges[i]:edges[i + 1]]), range(parts)))
+
+
+def second_order_host(prob, slab_bytes=256 << 20, out=None):
+    """The whole (T, 4, nk) float64 trajectory in (page-locked) host memory.  Time windows
+    ping-pong through two device slabs: the device->host copy of window w overlaps the
+    integration of window w+1 and -- when the source term lives on the host (a large NumPy array) --
+    the host->device copy of the source rows of window w+2, staged through page-locked buffers, so
+    both PCIe directions are busy at once instead of "upload everything, solve, download".
+    State is carried on the device between windows; results are bit-identical to one launch."""
+    from concurrent.futures import ThreadPoolExecutor
     T, nk = prob.T, prob.nk
-    out = np.empty((T, 4, nk), dtype=np.float64)
-    rows = max(1, min(T, slab_bytes // (32 * nk)))
+    if out is None:
+        out = _pinned_empty((T, 4, nk), torch.float64)
+    elif (not torch.is_tensor(out) or tuple(out.shape) != (T, 4, nk) or out.dtype != torch.float64
+          or not out.is_contiguous() or out.device.type != "cpu"):
+        raise ValueError("output buffer must be a contiguous float64 CPU tensor of shape %r" % ((T, 4, nk),))
+    W = max(1, min(T, slab_bytes // (32 * nk)))
+    streaming = prob.source_host is not None
+    prob.state.zero_()
     with torch.cuda.device(prob.dev):
-        slab = torch.empty((rows, 4, nk), dtype=torch.float64, device=prob.dev)
-        for t0 in range(0, T, rows):
-            t1 = min(T, t0 + rows)
-            prob.launch(t0, t1, slab, 1)
-            out[t0:t1] = slab[: t1 - t0].cpu().numpy()
-    prob.d2h_bytes = out.nbytes
-    return out
+        compute = torch.cuda.current_stream()
+        d2h, h2d = torch.cuda.Stream(), torch.cuda.Stream()
+        res = [torch.empty((W, 4, nk), dtype=torch.float64, device=prob.dev) for _ in range(2 if W < T else 1)]
+        freed = [None] * len(res)                         # result slab b copied out
+        src_dev = stage = None
+        pool = None
+        if streaming:
+            nsrc = max(prob.source_rows(t0, min(T, t0 + W))[1] - prob.source_rows(t0, min(T, t0 + W))[0]
+                       for t0 in range(0, T, W))
+            nsrc = max(nsrc, 1)
+            src_dev = [torch.empty((nsrc, nk), dtype=torch.complex128, device=prob.dev) for _ in range(2)]
+            pinned_src = prob.source_host.is_pinned()
+            if not pinned_src:
+                stage = [_pinned_empty((nsrc, nk), torch.complex128) for _ in range(2)]
+                pool = ThreadPoolExecutor(max_workers=4)
+            uploaded = [None, None]                       # H2D into src_dev[b] done
+            consumed = [None, None]                       # kernel that read src_dev[b] done
+            src_np = prob.source_host.numpy()
+
+            def upload(w):
+                """start the host->device copy of window w's source rows into slab w % 2"""
+                t0 = w * W
+                if t0 >= T:
+                    return
+                b = w % 2
+                r0, r1 = prob.source_rows(t0, min(T, t0 + W))
+                if r1 <= r0:
+                    uploaded[b] = (None, r0, 0)
+                    return
+                if consumed[b] is not None:
+                    h2d.wait_event(consumed[b])
+                if pinned_src:
+                    host_rows = prob.source_host[r0:r1]
+                else:
+                    if uploaded[b] is not None and uploaded[b][0] is not None:
+                        uploaded[b][0].synchronize()      # the staging buffer is free again
+                    _threaded_copy(stage[b].numpy()[: r1 - r0], src_np[r0:r1], pool)
+                    host_rows = stage[b][: r1 - r0]
+                with torch.cuda.stream(h2d):
+                    src_dev[b][: r1 - r0].copy_(host_rows, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(h2d)
+                prob.h2d_bytes += (r1 - r0) * nk * 16
+                uploaded[b] = (ev, r0, r1 - r0)
+            upload(0)
+            upload(1)
+        try:
+            for w, t0 in enumerate(range(0, T, W)):
+                t1 = min(T, t0 + W)
+                b = w % len(res)
+                if freed[b] is not None:
+                    compute.wait_event(freed[b])
+                window = None
+                if streaming:
+                    ev, r0, n = uploaded[w % 2]
+                    if ev is not None:
+                        compute.wait_event(ev)
+                        window = (src_dev[w % 2][:n], r0)
+                    else:
+                        window = (src_dev[w % 2][:1], r0)     # a window that takes no step reads nothing
+                prob.launch(t0, t1, res[b], 1, compute, source_window=window)
+                done = torch.cuda.Event()
+                done.record(compute)
+                if streaming:
+                    consumed[w % 2] = done
+                    upload(w + 2)
+                d2h.wait_event(done)
+                with torch.cuda.stream(d2h):
+                    out[t0:t1].copy_(res[b][: t1 - t0], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(d2h)
+                freed[b] = ev
+            d2h.synchronize()
+            compute.synchronize()
+            h2d.synchronize()
+        finally:
+            if pool is not None:
+                pool.shutdown(wait=True)
+    prob.d2h_bytes = T * 4 * nk * 8
+    return out.numpy()
 
 
 def so_derivs_device(model, y, t, k, fo_bg0, bgepsilon, fo_simtstart, fo_tstep, so_tstep, source_row=None,

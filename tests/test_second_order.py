@@ -332,6 +332,12 @@ def test_second_order_launch_properties():
     assert np.array_equal(engine.second_order_host(
         engine.SecondOrderProblem(pm, k, tsix, ystart, float(g["fo_tresult"][0]), T, h, source=src, **common),
         slab_bytes=32 * nk * 999), full, equal_nan=True)
+    # the same with a page-locked source tensor (streamed without staging) and short windows
+    pinned = torch.from_numpy(src).pin_memory()
+    prob = engine.SecondOrderProblem(pm, k, tsix, ystart, float(g["fo_tresult"][0]), T, h, source=pinned, **common)
+    assert prob.source is None and prob.source_host is not None          # 130 MB: streamed, not resident
+    assert np.array_equal(engine.second_order_host(prob, slab_bytes=32 * nk * 57), full, equal_nan=True)
+    assert prob.h2d_bytes >= src.nbytes * 0.7 and prob.d2h_bytes == full.nbytes
     strided = solve(src, every=37)
     assert np.array_equal(strided, full[::37], equal_nan=True)
     zero = np.zeros((4, nk))
