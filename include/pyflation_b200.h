@@ -117,6 +117,11 @@ int pf_potential_eval(const pf_model *m, int64_t n, const double *y_dev, double 
 int pf_derivs(const pf_model *m, int first_order, int64_t ncol, const double *y_dev, double t,
               const double *k_dev, double *dydx_dev, void *stream);
 
+/* Sum of n <= 128 host doubles in the order the kernels use for sums over fields -- NumPy's
+ * float64 add-reduce (eight running sums, a tree, the remainder in order): np.sum in
+ * cmpotentials.py:837 and cosmomodels.py:569.  NaN for n outside 0..128. */
+double pf_np_sum(const double *a_host, int n);
+
 /* ---- sizes ---- */
 int64_t pf_number_of_steps(double simtstart, double tend, double h);  /* rk4.py:73 */
 int64_t pf_nvar(int nfields);                      /* 2 nf^2 + 2 nf + 1 */

@@ -27,7 +27,7 @@ EXPORTS = [
     "pf_rec_doubles", "pf_rec_bg_offset", "pf_bg_run", "pf_stage_table", "pf_fo_run", "pf_solve_scratch_doubles",
     "pf_fo_solve", "pf_pr_spectrum", "pf_pr_spectrum_pert", "pf_scatter_slab", "pf_copy_rows_d2h", "pf_copy_window_d2h",
     "pf_host_fill_background", "pf_crossing_rows", "pf_bunch_davies", "pf_derivs",
-    "pf_so_run", "pf_so_derivs",
+    "pf_so_run", "pf_so_derivs", "pf_np_sum",
     "pf_fp64_peak_probe", "pf_peer_alloc", "pf_peer_free", "pf_peer_export", "pf_peer_open", "pf_peer_close",
 ]
 
@@ -79,6 +79,8 @@ def lib():
     L.pf_potential_param_default.argtypes = [c_int, c_int]
     L.pf_potential_param_default.restype = c_dbl
     L.pf_potential_eval.argtypes = [mp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]
+    L.pf_np_sum.argtypes = [ctypes.POINTER(c_dbl), c_int]
+    L.pf_np_sum.restype = c_dbl
     L.pf_number_of_steps.argtypes = [c_dbl, c_dbl, c_dbl]
     L.pf_number_of_steps.restype = c_i64
     L.pf_nvar.argtypes = [c_int]

@@ -204,6 +204,12 @@ extern "C" int64_t pf_number_of_steps(double simtstart, double tend, double h) {
     // int(np.around((tend - simtstart)/h) + 1): around = round-half-to-even = nearbyint
     return (int64_t)(nearbyint((tend - simtstart) / h) + 1.0);
 }
+// the summation order the kernels use for sums over fields (np_sum, pf_common.cuh), on the host:
+// lets the CPU test-suite pin it against np.sum without a GPU
+extern "C" double pf_np_sum(const double* a_host, int n) {
+    if (!a_host || n < 0 || n > 128) return __builtin_nan("");
+    return np_sum(n, [&](int i) { return a_host[i]; });
+}
 extern "C" int64_t pf_nvar(int nfields) { return nvar_of(nfields); }
 extern "C" int64_t pf_rec_doubles(int nfields) { return rec_of(nfields); }
 extern "C" int64_t pf_rec_bg_offset(int nfields) { return rec_bg_offset(nfields); }

@@ -184,3 +184,29 @@ def test_peer_and_probe_entries_reject_bad_arguments():
     m.potential_id, m.nfields = 0, 1
     assert L.pf_fo_run(ctypes.byref(m), 8, None, None, None, None, 10, 0.01, 0, 10, None, None, 0, 0, 4,
                        None, None) == -1
+
+
+def test_field_sums_round_like_numpy():
+    """The kernels add the terms of a sum over fields in NumPy's order (np_sum in pf_common.cuh =
+    DOUBLE_pairwise_sum: straight for fewer than 8 terms, else eight running sums, a tree, the
+    remainder).  pf_np_sum runs the same template on the host: bit-equal to np.sum for every
+    length a field count can take, also for the axis-0 reduction of an (n, 1) array
+    (cosmomodels.py:569), and different from plain left-to-right addition for n >= 8."""
+    import ctypes
+    from pyflation_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.RandomState(12)
+    differs = 0
+    for n in range(0, 65):
+        for _ in range(40):
+            a = np.ascontiguousarray(rng.uniform(0.1, 5.0, n) ** 2 * 1e-11)
+            got = L.pf_np_sum(a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n)
+            assert got == np.sum(a), (n, got, np.sum(a))
+            if n:
+                assert got == np.sum(a[:, None], axis=0)[0]
+            seq = 0.0
+            for x in a:
+                seq += x
+            differs += int(seq != got)
+    assert differs > 100                                # the order matters in practice
+    assert np.isnan(L.pf_np_sum(None, 3)) and np.isnan(L.pf_np_sum(a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 129))
