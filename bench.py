@@ -458,6 +458,30 @@ def measure_second_order(hbm_peak, reps=3, device_index=0):
         alg_bytes = mode_steps * 64.0
         all_bytes = mode_steps * 32.0 + float(T) * nk * 32.0
         del out, prob
+        # the reference's CPU path beside it (the cpu_baseline leg: NumPy port of rkdriver_tsix +
+        # CanonicalRampedSecondOrder.derivs, one core, the first 256 modes of the same grid)
+        cpu = None
+        try:
+            if os.path.join(ROOT, "oracle") not in sys.path:
+                sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import pyflation_oracle as O
+            ns = 256
+            fo_y = np.full((T_fo, 5, ns), np.nan, dtype=complex)
+            bg_rows = m.bgmodel.yresult[:T_fo, :, 0]
+            for col in range(ns):
+                fo_y[m.fotstartindex[col]:, 0:3, col] = bg_rows[m.fotstartindex[col]:]
+            t_cpu = time.perf_counter()
+            _, y_cpu, ts_cpu = O.second_order_run("lambdaphi4", {"nfields": 1}, k[:ns], m.ainit, np.arange(T_fo) * H,
+                                                  fo_y, m.fotstart[:ns], m.fotstartindex[:ns], m.bgepsilon,
+                                                  src[:, :ns].cpu().numpy(), H, 0.0, ramp=ramp)
+            cpu_wall = time.perf_counter() - t_cpu
+            assert np.array_equal(ts_cpu, tsix[:ns]) and np.isfinite(y_cpu[-1]).all()
+            cpu = {"value": float(np.sum(T - 1 - tsix[:ns])) / cpu_wall, "unit": "k-mode second-order RK4-steps/s",
+                   "cores": 1, "kind": "port", "wall_s": cpu_wall,
+                   "sample": "first %d modes of the grid, full T=%d trajectory, NumPy oracle port" % (ns, T)}
+            del fo_y, y_cpu
+        except Exception as err:
+            cpu = {"error": repr(err)}
         # end to end through the host path: source term in page-locked host memory in, trajectory in
         # page-locked host memory out, both streamed through time windows (engine.second_order_host)
         e2e = None
@@ -502,7 +526,7 @@ def measure_second_order(hbm_peak, reps=3, device_index=0):
         except Exception:
             pass
         return {"workload": name, "nk": nk, "T": T, "value": mode_steps / (ms * 1e-3), "ms": ms,
-                "unit": "k-mode second-order RK4-steps/s", "mode_kernel_ms": ms, "e2e": e2e,
+                "unit": "k-mode second-order RK4-steps/s", "mode_kernel_ms": ms, "e2e": e2e, "cpu_baseline": cpu,
                 "output_policy": "full trajectory", "clocks": sampler.result(),
                 "roofline": {"bound": "hbm", "frac": alg_bytes / (ms * 1e-3) / 1e9 / hbm_peak, "timed": "mode kernel",
                              "hbm": {"achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
