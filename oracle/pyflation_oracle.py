@@ -3,7 +3,9 @@
 A NumPy restatement of the reference's algorithm for the path this repository accelerates
 (fixed-step RK4 over a batch of k-modes that each start at their own time index, the
 canonical background / first-order right-hand sides, the ``cmpotentials`` functions, the
-horizon-crossing / Bunch-Davies initial-condition glue and the ``P_R`` reduction).
+horizon-crossing / Bunch-Davies initial-condition glue and the ``P_R`` reduction), plus the
+second-order stage that reuses the same driver (``CanonicalSecondOrder`` /
+``CanonicalRampedSecondOrder`` right-hand sides, ``SOCanonicalThreeStage`` set-up).
 
 Who may use it: ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
 ``--impl reference`` legs of ``bench.py`` -- as the checker or the timed CPU arm, never as
@@ -13,7 +15,9 @@ Parity status: PINNED.  ``tests/golden/*.npz`` hold outputs of the unmodified re
 in the build container through ``oracle/ref_shim.py`` (generator: ``tests/golden/make_golden.py``);
 ``tests/test_oracle_golden.py`` checks every function here against them, together with the
 reference's own known answers (``cosmomodels.py:2043`` ainit, ``solutions/fixtures.py:18``
-etainit, ``analysis/test/test_adiabatic.py:81-260`` P_R / Pphi vectors).
+etainit, ``analysis/test/test_adiabatic.py:81-260`` P_R / Pphi vectors).  The second-order functions
+are pinned the same way (``tests/golden/so_*.npz``: the reference's ``SOCanonicalThreeStage`` runs and
+single ``derivs`` calls; ``tests/test_second_order.py`` -- bit-identical on them).
 
 All ``file:line`` citations are relative to the reference tree.  The arithmetic mirrors the
 reference deliberately (complex128 carried for every row, each column integrating its own

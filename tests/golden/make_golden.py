@@ -10,6 +10,9 @@ Each ``fo_<name>.npz`` holds a sub-sampled first-order run of the reference
 the k sub-grid (always containing column 0 of the full grid), the start indices, the
 initial conditions, a set of trajectory rows (every ``row_stride``-th row, every row
 around each column's start index, and the last rows) and the final ``P_R`` spectra.
+``so_<name>.npz`` holds a second-order run on top of one of them: ``SOCanonicalThreeStage`` with
+``CanonicalSecondOrder`` and ``CanonicalRampedSecondOrder``, ``oracle.synthetic_source`` as the source
+term, plus single ``derivs`` calls of the three second-order classes.
 ``potentials.npz`` holds every ``cmpotentials`` function evaluated at fixed points.
 ``kat_adiabatic.npz`` restates the reference's own known-answer vectors for P_R
 (``analysis/test/test_adiabatic.py:81-260``) with the answers recomputed by the reference.
