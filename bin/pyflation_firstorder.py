@@ -4,7 +4,8 @@
 Drop-in for the reference's bin/pyflation_firstorder.py (:51-216): same options (-f/--filename,
 -p/--potential, -q/-v/--debug/--console), same ``runfomodel(filename, foargs, foclass)`` entry,
 fixtures and k range from ``run_config``; the integration runs on the GPU.  Results are written
-as ``.npz`` (the reference's HDF5 format is out of scope); extra option
+in the reference's HDF5 layout (pyflation_b200.hdf5lite; a file name ending in ``.npz`` selects a
+NumPy archive instead); extra option
 ``--kstride N`` keeps every N-th k of the range, ``--rowstride N`` every N-th time row.
 """
 import logging

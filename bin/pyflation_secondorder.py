@@ -6,7 +6,7 @@ Drop-in for the reference's bin/pyflation_secondorder.py (:43-170): same options
 The first-order file must carry the source term (dataset ``sourceterm``; the reference merges it in
 with bin/pyflation_source.py + pyflation_combine.py, here ``sohelpers.combine_source_and_fofile``;
 computing it is outside this package); the integration runs on the GPU (pf_so_run), results are
-written as ``.npz``.
+written in the reference's HDF5 layout (or as ``.npz`` when the file name ends so).
 """
 import logging
 import optparse

@@ -10,10 +10,12 @@ Second-order stage (cosmomodels.py:678-971, 1680-1946): ``CanonicalSecondOrder``
 ``CanonicalRampedSecondOrder``, ``CanonicalHomogeneousSecondOrder`` and the drivers
 ``SOCanonicalThreeStage`` / ``SOHorizonStart`` integrate on the GPU as well (pf_so_run) from a
 first-order model that carries a ``source`` array; computing that source term (the reference's
-``sourceterm`` package) is out of scope, as are the HDF5 results files.
+``sourceterm`` package) is out of scope.  Results files: the reference's HDF5 layout through
+:mod:`pyflation_b200.hdf5lite` (no PyTables here), or ``.npz`` archives with the same names.
 """
 import datetime
 import logging
+import os
 
 import numpy as np
 from scipy import interpolate
@@ -22,6 +24,7 @@ from .configuration import _debug
 from . import cmpotentials
 from . import rk4
 from . import analysis
+from . import hdf5lite
 
 module_logger = logging.getLogger(__name__)
 
@@ -136,16 +139,52 @@ class CosmologicalModel(object):
                 "datetime": datetime.datetime.now().strftime("%Y%m%d%H%M%S"),
                 "nfields": self.nfields}
 
-    def saveallresults(self, filename=None, filetype="npz", **kwargs):
-        """Save results.  The reference writes a PyTables HDF5 file (cosmomodels.py:236-402);
-        that format is outside this package's scope, so the same dataset names are written to
-        a NumPy ``.npz`` archive instead."""
+    def gethf5paramsdict(self):
+        """Columns of the ``parameters`` table of a results file (cosmomodels.py:221-234)."""
+        return {"solver": hdf5lite.StringCol(50),
+                "classname": hdf5lite.StringCol(255),
+                "tstart": hdf5lite.Float64Col(np.shape(self.tstart)),
+                "simtstart": hdf5lite.Float64Col(),
+                "tend": hdf5lite.Float64Col(),
+                "tstep_wanted": hdf5lite.Float64Col(),
+                "datetime": hdf5lite.Float64Col(),
+                "nfields": hdf5lite.IntCol()}
+
+    def saveallresults(self, filename=None, filetype=None, yresultshape=None, **kwargs):
+        """Save the results of the last run (cosmomodels.py:236-277).
+
+        ``filetype`` "hf5" writes the reference's HDF5 layout -- groups ``results`` /
+        ``bgresults``, extendable ``yresult`` / ``tresult`` arrays, the ``parameters`` and
+        ``pot_params`` tables, an existing file is appended to -- through
+        :mod:`pyflation_b200.hdf5lite` (PyTables is not available here); "npz" writes the same
+        dataset names into a NumPy archive.  With no ``filetype`` the file name's extension
+        decides, and a missing file name means ``run<datetime>.hf5`` as in the reference."""
         if self.yresult is None:
             raise ModelError("No results to save yet.")
-        if filetype != "npz":
-            raise NotImplementedError("only filetype='npz' is available (HDF5 output is out of scope)")
-        if filename is None:
-            filename = "run" + datetime.datetime.now().strftime("%Y%m%d%H%M%S") + ".npz"
+        if filetype is None:
+            ext = os.path.splitext(filename)[1].lower() if filename else ".hf5"
+            filetype = {".npz": "npz", ".hf5": "hf5", ".h5": "hf5", ".hdf5": "hf5", ".hdf": "hf5"}.get(ext, "npz")
+        if filetype not in ("npz", "hf5"):
+            raise NotImplementedError("Saving results in format %s is not implemented." % filetype)
+        if not filename:
+            now = (getattr(self, "lastparams", None) or self.callingparams())["datetime"]
+            filename = os.path.join(os.getcwd(), "run" + now + "." + filetype)
+            self._log.info("Filename set to " + filename)
+        if not os.path.isdir(os.path.dirname(os.path.abspath(filename))):
+            raise IOError("Directory %s does not exist" % os.path.dirname(filename))
+        if filetype == "hf5":
+            grpname = "bgresults" if getattr(self, "k", None) is None else "results"      # :263-267
+            if yresultshape is None:
+                yresultshape = [0] + list(np.shape(self.yresult))[1:]
+            if os.path.isfile(filename) and hdf5lite.is_hdf5_file(filename):
+                rf = hdf5lite.open_file(filename, "a")                                  # append mode (:247-249)
+            else:
+                rf = self.createhdf5structure(filename, grpname, yresultshape, **kwargs)
+            try:
+                self.saveresultsinhdf5(rf, grpname)
+            finally:
+                rf.close()
+            return filename
         data = dict(yresult=self.yresult, tresult=self.tresult)
         for name in ("k", "ystart", "bgystart", "foystart", "fotstart", "fotstartindex", "ainit"):
             if getattr(self, name, None) is not None:
@@ -153,11 +192,9 @@ class CosmologicalModel(object):
         if getattr(self, "bgmodel", None) is not None:
             data["bg_tresult"] = self.bgmodel.tresult
             data["bg_yresult"] = self.bgmodel.yresult
-        if getattr(self, "source", None) is not None and not isinstance(self, SOCanonicalThreeStage):
-            # the reference keeps the second-order source term next to the first-order results
-            # (results.sourceterm, cosmomodels.py:1607-1612)
-            src = self.source
-            data["sourceterm"] = src.cpu().numpy() if hasattr(src, "cpu") else np.asarray(src)
+        src = self._source_for_file()
+        if src is not None:
+            data["sourceterm"] = src
         for name in ("potential_func", "nfields", "tend", "tstep_wanted", "simtstart", "cq"):
             if getattr(self, name, None) is not None:
                 data["param_" + name] = np.asarray(getattr(self, name))
@@ -167,6 +204,79 @@ class CosmologicalModel(object):
         data["classname"] = np.asarray(self.__class__.__name__)
         np.savez(filename, **data)
         return filename
+
+    def _source_for_file(self):
+        """The second-order source term a first-order model carries, as a host array: the
+        reference keeps it next to the first-order results (results.sourceterm, :1607-1612)."""
+        src = getattr(self, "source", None)
+        if src is None or isinstance(self, SOCanonicalThreeStage):
+            return None
+        return src.cpu().numpy() if hasattr(src, "cpu") else np.asarray(src)
+
+    def createhdf5structure(self, filename, grpname="results", yresultshape=None, hdf5complevel=0,
+                            hdf5complib="zlib"):
+        """A new HDF5 file with the reference's structure (cosmomodels.py:279-349); returns the open
+        file.  The reference compresses with blosc, level 2, which is a PyTables plug-in and not
+        an HDF5 codec: the default here is no compression, ``hdf5complevel`` > 0 uses zlib."""
+        rf = hdf5lite.open_file(filename, "w")
+        try:
+            filters = hdf5lite.Filters(complevel=hdf5complevel, complib=hdf5complib)
+            resgroup = rf.create_group(rf.root, grpname, "Results of simulation")
+            rf.create_earray(resgroup, "tresult", hdf5lite.Float64Atom(), (0,), filters=filters, expectedrows=8194)
+            rf.create_table(resgroup, "parameters", self.gethf5paramsdict(), filters=filters)
+            rf.create_table(resgroup, "pot_params", {"name": hdf5lite.StringCol(255),
+                                                     "value": hdf5lite.Float64Col()}, filters=filters)
+            if grpname == "results":
+                if getattr(self, "bgmodel", None) is not None:
+                    bggrp = rf.create_group(rf.root, "bgresults", "Background results")
+                    rf.create_array(bggrp, "tresult", np.asarray(self.bgmodel.tresult))
+                    rf.create_array(bggrp, "yresult", np.asarray(self.bgmodel.yresult))
+                rf.create_earray(resgroup, "yresult", hdf5lite.ComplexAtom(itemsize=16), tuple(yresultshape),
+                                 filters=filters, expectedrows=8194)
+                rf.create_array(resgroup, "k", np.asarray(self.k))
+                if getattr(self, "ystart", None) is not None:
+                    rf.create_array(resgroup, "ystart", np.asarray(self.ystart))
+                if getattr(self, "bgystart", None) is not None:
+                    rf.create_array(resgroup, "bgystart", np.asarray(self.bgystart))
+                for name in ("foystart", "fotstart", "fotstartindex"):
+                    if getattr(self, name, None) is not None:
+                        rf.create_array(resgroup, name, np.asarray(getattr(self, name)))
+                src = self._source_for_file()
+                if src is not None:                     # what the wrapper reads back (:1607-1612)
+                    rf.create_array(resgroup, "sourceterm", src)
+            else:
+                rf.create_earray(resgroup, "yresult", hdf5lite.Float64Atom(), tuple(yresultshape),
+                                 filters=filters, expectedrows=8300)
+        except Exception:
+            rf.isopen = False                           # nothing useful to write
+            raise
+        return rf
+
+    def saveresultsinhdf5(self, rf, grpname="results"):
+        """Append this run to the open results file (cosmomodels.py:351-402)."""
+        resgrp = rf.get_node(rf.root, grpname)
+        paramstab = resgrp.parameters
+        row = paramstab.row
+        params = self.callingparams()
+        for key in params:
+            if key in paramstab.colnames:
+                row[key] = params[key]
+        for key in ("simtstart", "cq"):                  # columns beyond the calling parameters
+            if key in paramstab.colnames and getattr(self, key, None) is not None:
+                row[key] = getattr(self, key)
+        row.append()
+        paramstab.flush()
+        potparamstab = resgrp.pot_params
+        for key in self.pot_params or {}:
+            row = potparamstab.row
+            row["name"] = key
+            row["value"] = self.pot_params[key]
+            row.append()
+        potparamstab.flush()
+        yres = np.asarray(self.yresult)
+        resgrp.yresult.append(yres if yres.dtype == resgrp.yresult.dtype else yres.astype(resgrp.yresult.dtype))
+        resgrp.tresult.append(np.asarray(self.tresult, dtype=np.float64))
+        rf.flush()
 
 
 class PhiModels(CosmologicalModel):
@@ -448,6 +558,16 @@ class MultiStageDriver(CosmologicalModel):
                 "classname": self.__class__.__name__,
                 "datetime": datetime.datetime.now().strftime("%Y%m%d%H%M%S"),
                 "nfields": self.nfields}
+
+
+    def gethf5paramsdict(self):
+        """cosmomodels.py:1213-1227, plus ``cq`` (the reference does not store it and falls back
+        to the constructor's default when a file is wrapped)."""
+        params = super(MultiStageDriver, self).gethf5paramsdict()
+        params.update({"ainit": hdf5lite.Float64Col(),
+                       "potential_func": hdf5lite.StringCol(255),
+                       "cq": hdf5lite.Float64Col()})
+        return params
 
 
 class FOCanonicalTwoStage(MultiStageDriver):
@@ -812,14 +932,57 @@ class SOHorizonStart(SOCanonicalThreeStage):
         self._finish_init(soclass)
 
 
+class _ResultsFromHDF5(dict):
+    """The datasets of a results file in the reference's HDF5 layout (cosmomodels.py:279-349),
+    under the names the ``.npz`` archives use, so that both kinds of file are wrapped by the same
+    code.  Read as in the reference's wrapper (:1584-1622): ``results.parameters[0]`` for the
+    calling parameters, ``results.pot_params`` row by row, ``bgresults`` for the background."""
+
+    files = property(lambda self: list(self))
+
+    def __init__(self, filename):
+        dict.__init__(self)
+        text = lambda v: v.decode("utf-8", "replace") if isinstance(v, bytes) else str(v)
+        with hdf5lite.open_file(filename, "r") as rf:
+            try:
+                results = rf.root.results
+                params = results.parameters
+                for name in ("yresult", "tresult", "k"):
+                    self[name] = getattr(results, name).read()
+            except hdf5lite.NoSuchNodeError:
+                raise ModelError("File does not contain correct model data structure!")
+            for name in ("fotstart", "foystart", "ystart", "bgystart", "fotstartindex", "sourceterm"):
+                if name in results:
+                    self[name] = getattr(results, name).read()
+            first = params[0]
+            self["classname"] = np.asarray(text(first["classname"]))
+            for col in params.colnames:
+                if col in ("potential_func",):
+                    self["param_" + col] = np.asarray(text(first[col]))
+                elif col in ("nfields", "tend", "tstep_wanted", "simtstart", "cq"):
+                    self["param_" + col] = np.asarray(first[col])
+                elif col == "ainit":
+                    self["ainit"] = np.asarray(first[col])
+            if "pot_params" in results:
+                rows = results.pot_params.read()
+                self["pot_param_keys"] = np.array([text(r["name"]) for r in rows])
+                self["pot_param_vals"] = np.array([float(r["value"]) for r in rows])
+            if "bgresults" in rf.root:
+                self["bg_tresult"] = rf.root.bgresults.tresult.read()
+                self["bg_yresult"] = rf.root.bgresults.yresult.read()
+
+
 def make_wrapper_model(modelfile, *args, **kwargs):
     """Return a model instance holding the results stored in ``modelfile`` (the counterpart of
     ``saveallresults``; the reference's version reads its HDF5 files, cosmomodels.py:1552-1677,
-    this one reads the ``.npz`` archives written here)."""
-    import os
+    this one reads those too -- through :mod:`pyflation_b200.hdf5lite` -- and the ``.npz`` archives
+    written here).  The arrays are read into memory and the file is closed."""
     if not os.path.isfile(modelfile):
         raise IOError("File does not exist!")
-    z = np.load(modelfile, allow_pickle=False)
+    if hdf5lite.is_hdf5_file(modelfile):
+        z = _ResultsFromHDF5(modelfile)
+    else:
+        z = np.load(modelfile, allow_pickle=False)
     classname = str(z["classname"]) if "classname" in z.files else "FOCanonicalTwoStage"
     cls = globals().get(classname, FOCanonicalTwoStage)
     if issubclass(cls, SOCanonicalThreeStage):

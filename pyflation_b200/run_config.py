@@ -51,12 +51,15 @@ kend = getkend(kinit, deltak, numsoks)
 foclass = c.FOCanonicalTwoStage
 
 RESULTSDIR = os.path.join(os.getcwd(), "results")
-foresults = os.path.join(RESULTSDIR, "fo.npz")
+# results file names (run_config.py:252-261): HDF5 in the reference's layout; a name ending in
+# ".npz" makes the scripts write / read NumPy archives instead
+foresults = os.path.join(RESULTSDIR, "fo.hf5")
+srcresults = os.path.join(RESULTSDIR, "src.hf5")
 
 # second-order stage (run_config.py:178-181, 215-217, 258-260): the ramped class is the default
 soclass = c.CanonicalRampedSecondOrder
 soargs = {"solver": "rkdriver_tsix",
           "nfields": 1,                 # only single field models can have second order calculated
           "soclass": soclass}
-mrgresults = os.path.join(RESULTSDIR, "mrg.npz")
-soresults = os.path.join(RESULTSDIR, "so.npz")
+mrgresults = os.path.join(RESULTSDIR, "mrg.hf5")
+soresults = os.path.join(RESULTSDIR, "so.hf5")

@@ -279,23 +279,41 @@ def test_partition_property():
     check()
 
 
-def test_save_and_wrapper_model_roundtrip(tmp_path):
-    """saveallresults -> make_wrapper_model (npz counterpart of cosmomodels.py:236-402, 1552-1677),
-    with results injected the way the reference's tests do."""
+@pytest.mark.parametrize("ext", [".npz", ".hf5"])
+def test_save_and_wrapper_model_roundtrip(tmp_path, ext):
+    """saveallresults -> make_wrapper_model (cosmomodels.py:236-402, 1552-1677) through the
+    reference's HDF5 layout and through the .npz counterpart, with results injected the way the
+    reference's tests do."""
     from pyflation_b200 import cosmomodels as c
     g = load_fo("c3_hybridquadratic_2p20")
     m = c.FOCanonicalTwoStage(k=g["k"], nfields=2, potential_func="hybridquadratic",
                               pot_params={"nfields": 2}, bgystart=g["bgystart"].copy(), cq=50)
     m.yresult, m.tresult = g["yrows"], g["tresult"][g["rows"]]
     m.foystart, m.fotstartindex, m.fotstart, m.ainit = g["foystart"], g["fotstartindex"], g["fotstart"], g["ainit"]
-    path = m.saveallresults(filename=str(tmp_path / "run.npz"))
+    path = m.saveallresults(filename=str(tmp_path / ("run" + ext)))
     w = c.make_wrapper_model(path)
     assert isinstance(w, c.FOCanonicalTwoStage) and w.nfields == 2 and w.potential_func == "hybridquadratic"
     assert np.array_equal(w.k, g["k"]) and np.array_equal(w.fotstartindex, g["fotstartindex"])
     assert np.array_equal(w.yresult.view(np.float64), m.yresult.view(np.float64), equal_nan=True)
     assert rel_err(w.Pr[-1:], g["Pr_last"]) < 1e-12
     with pytest.raises(IOError):
-        c.make_wrapper_model(str(tmp_path / "missing.npz"))
+        c.make_wrapper_model(str(tmp_path / ("missing" + ext)))
+    with pytest.raises(IOError):
+        m.saveallresults(filename=str(tmp_path / "no_such_dir" / ("run" + ext)))
+    with pytest.raises(NotImplementedError):
+        m.saveallresults(filename=str(tmp_path / "run.txt"), filetype="txt")
+    if ext == ".hf5":
+        # an existing file is appended to, as in the reference (cosmomodels.py:247-249): two runs
+        assert m.saveallresults(filename=path) == path
+        w2 = c.make_wrapper_model(path)
+        assert w2.yresult.shape[0] == 2 * m.yresult.shape[0] and len(w2.tresult) == 2 * len(m.tresult)
+        # zlib-compressed files read back the same
+        packed = m.saveallresults(filename=str(tmp_path / "packed.hf5"), hdf5complevel=2)
+        assert os.path.getsize(packed) < os.path.getsize(path) // 2
+        w3 = c.make_wrapper_model(packed)
+        assert np.array_equal(w3.yresult.view(np.float64), m.yresult.view(np.float64), equal_nan=True)
+        with pytest.raises(NotImplementedError):
+            m.saveallresults(filename=str(tmp_path / "blosc.hf5"), hdf5complevel=2, hdf5complib="blosc")
 
 
 def test_committed_bench_record_has_contract_keys():

@@ -132,10 +132,12 @@ def test_driver_setup_matches_reference_without_gpu():
         c.SOHorizonStart(m)
 
 
-def test_results_file_carries_the_source_term(tmp_path):
+@pytest.mark.parametrize("ext", [".npz", ".hf5"])
+def test_results_file_carries_the_source_term(tmp_path, ext):
     """The reference's second-order script wraps a first-order results file that carries the
     source term (results.sourceterm -> model.source, bgepsilon recomputed; cosmomodels.py:1607-1661)
-    and hands it to SOCanonicalThreeStage: same round trip through the .npz counterpart."""
+    and hands it to SOCanonicalThreeStage: the same round trip through the reference's HDF5 layout
+    (hdf5lite) and through the .npz counterpart."""
     from pyflation_b200 import cosmomodels as c
     g = load_so("so_msqphisq")
     m = injected_first_order(g)
@@ -143,24 +145,37 @@ def test_results_file_carries_the_source_term(tmp_path):
                                potential_func=g["potential"], pot_params=dict(g["params"]), nfields=1)
     bg.tresult, bg.yresult = m.tresult, np.nan_to_num(g["fo_bg0"])[:, :, None]
     m.bgmodel = bg
-    path = m.saveallresults(filename=str(tmp_path / "fo.npz"))
+    path = m.saveallresults(filename=str(tmp_path / ("fo" + ext)))
+    if ext == ".hf5":
+        from pyflation_b200 import hdf5lite
+        with hdf5lite.open_file(path) as rf:               # the reference's layout (:279-349)
+            assert sorted(rf.root._v_children) == ["bgresults", "results"]
+            assert sorted(rf.root.results._v_children) == [
+                "bgystart", "fotstart", "fotstartindex", "k", "parameters", "pot_params",
+                "sourceterm", "tresult", "yresult", "ystart"]
+            assert rf.root.results.yresult.kind == "EARRAY" and rf.root.results.yresult.dtype == np.complex128
+            assert rf.root.results.parameters[0]["classname"] == b"FOCanonicalTwoStage"
+            assert sorted(rf.root.bgresults._v_children) == ["tresult", "yresult"]
     w = c.make_wrapper_model(path)
     assert np.array_equal(w.source, m.source) and w.bgepsilon.shape == (len(m.tresult),)
+    assert np.array_equal(w.yresult.view(np.float64), np.asarray(m.yresult).view(np.float64), equal_nan=True)
+    assert w.potential_func == m.potential_func and w.pot_params == m.pot_params and w.cq == m.cq
     so = c.SOCanonicalThreeStage(w, soclass=c.CanonicalRampedSecondOrder)
     assert np.array_equal(so.tstartindex, g["ramped_tstartindex"]) and so.source is w.source
     del m.source
-    w2 = c.make_wrapper_model(m.saveallresults(filename=str(tmp_path / "fo_nosource.npz")))
+    w2 = c.make_wrapper_model(m.saveallresults(filename=str(tmp_path / ("fo_nosource" + ext))))
     assert w2.source is None
     with pytest.raises(c.ModelError):
         c.SOCanonicalThreeStage(w2)
     so.yresult, so.tresult = g["ramped_yrows"], g["ramped_tresult"][g["ramped_rows"]]
-    sopath = so.saveallresults(filename=str(tmp_path / "so.npz"))
+    sopath = so.saveallresults(filename=str(tmp_path / ("so" + ext)))
     with pytest.raises(c.ModelError):
         c.make_wrapper_model(sopath)
 
 
-def test_combine_source_and_first_order_files(tmp_path):
-    """sohelpers.combine_source_and_fofile (sohelpers.py:20-86) on .npz files: the merged file is
+@pytest.mark.parametrize("ext,srcext", [(".npz", ".npz"), (".hf5", ".hf5"), (".hf5", ".npz")])
+def test_combine_source_and_first_order_files(tmp_path, ext, srcext):
+    """sohelpers.combine_source_and_fofile (sohelpers.py:20-86) on HDF5 / .npz files: the merged file is
     what make_wrapper_model + SOCanonicalThreeStage expect (first-order data cut to the source's k
     range, ``sourceterm`` added), with the reference's naming and checks."""
     import pyflation_oracle as oracle
@@ -172,26 +187,42 @@ def test_combine_source_and_first_order_files(tmp_path):
                                potential_func=g["potential"], pot_params=dict(g["params"]), nfields=1)
     bg.tresult, bg.yresult = m.tresult, np.nan_to_num(g["fo_bg0"])[:, :, None]
     m.bgmodel, m.foystart = bg, np.zeros((5, len(m.k)), dtype=complex)
-    fofile = m.saveallresults(filename=str(tmp_path / "fo.npz"))
+    fofile = m.saveallresults(filename=str(tmp_path / ("fo" + ext)))
     nks = 3                                              # the source covers the first 3 modes
     src = oracle.synthetic_source(m.tresult, m.k[:nks])
-    srcfile = str(tmp_path / "src-run1.npz")
-    np.savez(srcfile, sourceterm=src, k=m.k[:nks], nix=np.arange(len(m.tresult)))
+
+    def write_source(path, **data):
+        if path.endswith(".npz"):
+            np.savez(path, **data)
+        else:                                            # the source-term files' layout: /results/...
+            from pyflation_b200 import hdf5lite
+            with hdf5lite.open_file(path, "w") as sf:
+                grp = sf.create_group(sf.root, "results")
+                for name in data:
+                    sf.create_array(grp, name, data[name])
+        return path
+
+    srcfile = write_source(str(tmp_path / ("src-run1" + srcext)), sourceterm=src, k=m.k[:nks],
+                           nix=np.arange(len(m.tresult)))
     merged = sohelpers.combine_source_and_fofile(srcfile, fofile)
-    assert os.path.basename(merged) == "foandsrc-run1.npz" and os.path.isfile(merged)
+    assert os.path.basename(merged) == "foandsrc-run1" + srcext and os.path.isfile(merged)
     again = sohelpers.combine_source_and_fofile(srcfile, fofile)
-    assert os.path.basename(again) == "foandsrc_-run1.npz"
+    assert os.path.basename(again) == "foandsrc_-run1" + srcext
     w = c.make_wrapper_model(merged)
     assert w.yresult.shape[2] == nks and len(w.k) == nks and w.foystart.shape == (5, nks)
     assert np.array_equal(w.source, src) and np.array_equal(w.fotstartindex, g["fotstartindex"][:nks])
     so = c.SOCanonicalThreeStage(w)
     assert np.array_equal(so.tstartindex, g["plain_tstartindex"][:nks])
-    np.savez(str(tmp_path / "src-short.npz"), sourceterm=src[:10], k=m.k[:nks], nix=np.arange(10))
+    short = write_source(str(tmp_path / ("src-short" + srcext)), sourceterm=src[:10], k=m.k[:nks], nix=np.arange(10))
     with pytest.raises(ValueError):
-        sohelpers.combine_source_and_fofile(str(tmp_path / "src-short.npz"), fofile)
-    np.savez(str(tmp_path / "src-bad.npz"), k=m.k[:nks])
+        sohelpers.combine_source_and_fofile(short, fofile)
+    bad = write_source(str(tmp_path / ("src-bad" + srcext)), k=m.k[:nks])
     with pytest.raises(KeyError):
-        sohelpers.combine_source_and_fofile(str(tmp_path / "src-bad.npz"), fofile)
+        sohelpers.combine_source_and_fofile(bad, fofile)
+    assert sorted(os.listdir(str(tmp_path))) == sorted(
+        ["fo" + ext] + [n + srcext for n in ("src-run1", "foandsrc-run1", "foandsrc_-run1", "src-short", "src-bad")])
+    with pytest.raises(IOError):
+        sohelpers.combine_source_and_fofile(str(tmp_path / ("src-missing" + srcext)), fofile)
 
 
 def test_so_entry_points_reject_bad_arguments():
