@@ -383,3 +383,40 @@ def test_errors(tmp_path):
     f.close()
     with pytest.raises(h.ClosedFileError):
         f.create_group("/", "g")
+
+
+def test_reader_follows_object_header_continuation_blocks(tmp_path):
+    """libhdf5 moves messages that no longer fit (attributes added later: PyTables' TITLE, CLASS,
+    ...) into continuation blocks (message 0x0010).  The writer never needs one, so a file of its
+    own is rearranged by hand here: the last attribute of a dataset's header is moved to the end
+    of the file, a continuation message plus a NIL message take its place."""
+    fn = str(tmp_path / "c.h5")
+    with h.open_file(fn, "w") as f:
+        node = f.create_array("/", "x", np.arange(5.0), title="moved title")
+        node.attrs["zz_last"] = np.arange(3, dtype=np.int32)
+    raw = bytearray(open(fn, "rb").read())
+    with h.open_file(fn) as f:
+        addr = [a for n, a, c in f._img.group_entries(*struct.unpack_from("<QQ", raw, 80)) if n == "x"][0]
+        before = dict(f.root.x.attrs)
+    assert before["FLAVOR"] == "numpy" and before["zz_last"].tolist() == [0, 1, 2]
+    nmsg, _ref, size = struct.unpack_from("<HII", raw, addr + 2)
+    p, msgs = addr + 16, []
+    while p < addr + 16 + size:
+        t, n = struct.unpack_from("<HH", raw, p)
+        msgs.append((t, p, 8 + n))
+        p += 8 + n
+    t, at, length = msgs[-1]
+    assert t == 0x0C and length >= 32                          # an attribute: the last message
+    moved = bytes(raw[at:at + length])
+    new_at = len(raw)
+    raw[at:at + length] = (struct.pack("<HHB3x", 0x10, 16, 0) + struct.pack("<QQ", new_at, length)
+                           + struct.pack("<HHB3x", 0, length - 32, 0) + b"\0" * (length - 32))
+    raw += moved
+    struct.pack_into("<H", raw, addr + 2, nmsg + 2)
+    struct.pack_into("<Q", raw, 40, len(raw))                  # end-of-file address
+    open(fn, "wb").write(bytes(raw))
+    with h.open_file(fn) as f:
+        after = dict(f.root.x.attrs)
+        assert sorted(after) == sorted(before) and f.root.x.title == "moved title"
+        assert all(np.array_equal(after[q], before[q]) for q in before)
+        assert np.array_equal(f.root.x[:], np.arange(5.0))
