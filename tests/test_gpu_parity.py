@@ -630,17 +630,27 @@ def test_pr_kernel_known_answers():
                                g["block_Pr"] * (k.cpu().numpy() ** 3 / (2 * np.pi ** 2)), rtol=1e-13)
 
 
-def test_firstorder_script(tmp_path):
+@pytest.mark.parametrize("ext", [".npz", ".hf5"])
+def test_firstorder_script(tmp_path, ext):
     """bin/pyflation_firstorder.py (the caller of the hot path, reference bin/pyflation_firstorder.py):
-    default msqphisq fixture on every 64th k of the K4 range == BASELINE config 1's golden columns."""
+    default msqphisq fixture on every 64th k of the K4 range == BASELINE config 1's golden columns,
+    saved as a NumPy archive and in the reference's HDF5 layout."""
     import subprocess, sys
     from conftest import ROOT
     g = load_fo("c1_msqphisq_k4")
-    out = str(tmp_path / "fo.npz")
+    out = str(tmp_path / ("fo" + ext))
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "pyflation_firstorder.py"), "-f", out,
                           "-p", "msqphisq", "--kstride", "64", "--console", "-v"], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
-    z = np.load(out)
+    if ext == ".npz":
+        z = np.load(out)
+    else:
+        from pyflation_b200 import hdf5lite
+        with hdf5lite.open_file(out) as rf:
+            assert rf.root.results.parameters[0]["classname"] == b"FOCanonicalTwoStage"
+            assert rf.root.bgresults.yresult.shape[1:] == (3, 1)
+            z = {name: getattr(rf.root.results, name).read() for name in ("yresult", "k", "tresult")}
+        assert len(z["tresult"]) == g["T"]
     assert z["yresult"].shape == (g["T"], 5, 33)
     pick = cols = [0, 1, 2, 3, 4]                      # k indices 0, 64, ..., 256 are in both sub-grids
     assert np.array_equal(z["k"][pick], g["k"][cols])
