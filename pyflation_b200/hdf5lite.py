@@ -600,10 +600,14 @@ class Leaf(Node):
         if lay["class"] != 2:
             mm = self.memmap_stored()
             return np.array(mm[tuple(slice(a, b) for a, b in zip(lo, hi))])
+        if img.mm.closed:
+            raise ClosedFileError("dataset %s: the file %s is closed" % (self._v_name, img.filename))
         out = np.zeros(tuple(b - a for a, b in zip(lo, hi)), dtype=self.dtype)
         cshape = lay["chunk"]
         csize = int(np.prod(cshape)) * self.dtype.itemsize
-        for offs, nbytes, mask, addr in lay["index"]():
+        if "chunks" not in lay:                           # walk the chunk B-tree once per dataset
+            lay["chunks"] = lay["index"]()
+        for offs, nbytes, mask, addr in lay["chunks"]:
             c_lo = [max(o, a) for o, a in zip(offs, lo)]
             c_hi = [min(o + c, b, s) for o, c, b, s in zip(offs, cshape, hi, shape)]
             if any(a >= b for a, b in zip(c_lo, c_hi)):

@@ -420,3 +420,18 @@ def test_reader_follows_object_header_continuation_blocks(tmp_path):
         assert sorted(after) == sorted(before) and f.root.x.title == "moved title"
         assert all(np.array_equal(after[q], before[q]) for q in before)
         assert np.array_equal(f.root.x[:], np.arange(5.0))
+
+
+def test_nodes_of_a_closed_file(tmp_path):
+    fn = str(tmp_path / "closed.h5")
+    with h.open_file(fn, "w") as f:
+        f.create_earray("/", "chunked", h.Float64Atom(), (0,)).append(np.arange(9.0))
+        f.create_array("/", "plain", np.arange(4.0))
+    f = h.open_file(fn)
+    chunked, plain = f.root.chunked, f.root.plain
+    f.close()
+    with pytest.raises(h.ClosedFileError):
+        chunked[:]
+    assert plain[:].tolist() == [0.0, 1.0, 2.0, 3.0]         # contiguous data: its own memory map
+    with pytest.raises(h.ClosedFileError):
+        f.get_node("/plain")
