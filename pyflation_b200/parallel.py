@@ -4,9 +4,12 @@ The reference has no parallelism on this path (one Python process, SURVEY.md sec
 never interact (cosmomodels.py:663-674 couples only the fields of one k), so the B200 design
 shards the k grid: one process per GPU, each owning a contiguous k-slab, no communication
 during the integration (every rank recomputes the shared ~1 MB background table itself).  The
-only collective is the assembly of result rows -- a window of yresult, the last row, or P_R(k)
--- with one NCCL all-gather over NVLink followed by an on-GPU interleave into the reference
-layout [rows][nvar][nk] (k is the innermost axis, so rank slabs interleave row by row).
+only exchange is the assembly of result rows -- a window of yresult, the last row, or P_R(k) --
+into the reference layout [rows][nvar][nk] (k is the innermost axis, so rank slabs interleave row
+by row).  Two forms: ``PeerAssembly`` / ``ShardedFirstOrder.run_assembled`` (the product path:
+every rank's mode kernel stores straight into the assembling rank's buffer over NVLink, CUDA IPC
+peer memory -- compute and gather are one kernel), and ``gather_rows`` (one NCCL all-gather plus
+an on-GPU interleave; also the gloo path of the CPU tests).
 """
 import ctypes
 
