@@ -435,3 +435,89 @@ def test_nodes_of_a_closed_file(tmp_path):
     assert plain[:].tolist() == [0.0, 1.0, 2.0, 3.0]         # contiguous data: its own memory map
     with pytest.raises(h.ClosedFileError):
         f.get_node("/plain")
+
+
+def test_random_trees_round_trip_and_pass_the_audit(tmp_path):
+    """Property test (hypothesis): random group trees of arrays / extendable arrays / tables of
+    random dtypes, shapes, chunk shapes and filters are read back bit for bit and their bytes
+    satisfy the structural audit."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    dtypes = st.sampled_from([np.float64, np.float32, np.int64, np.int32, np.uint8, np.complex128,
+                              np.complex64, np.dtype("S7"), np.bool_])
+    names = st.text(alphabet="abcdefghijklmnopqrstuvwxyz_0123456789", min_size=1, max_size=12)
+
+    def array_of(dt, shape, seed):
+        rng = np.random.default_rng(seed)
+        dt = np.dtype(dt)
+        n = int(np.prod(shape))
+        if dt.kind == "c":
+            a = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        elif dt.kind == "S":
+            a = np.array([b"x" * int(v) for v in rng.integers(0, dt.itemsize + 1, n)], dtype=dt)
+        elif dt.kind == "b":
+            a = rng.integers(0, 2, n).astype(bool)
+        elif dt.kind in "iu":
+            a = rng.integers(0, 100, n)
+        else:
+            a = rng.standard_normal(n)
+        return np.asarray(a).astype(dt).reshape(shape)
+
+    leaf = st.tuples(st.sampled_from(["array", "earray", "table"]), dtypes,
+                     st.lists(st.integers(0, 5), min_size=0, max_size=3),
+                     st.lists(st.integers(1, 4), min_size=3, max_size=3),
+                     st.sampled_from([None, (1, True), (6, False)]), st.integers(0, 2 ** 31))
+    tree = st.dictionaries(names, st.one_of(leaf, st.dictionaries(names, leaf, max_size=11)), max_size=12)
+    counter = [0]
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(tree)
+    def check(spec):
+        counter[0] += 1
+        fn = str(tmp_path / ("t%d.h5" % counter[0]))
+        want = {}
+
+        def add(f, where, path, name, item):
+            kind, dt, shape, chunk, filt, seed = item
+            filters = None if filt is None else h.Filters(complevel=filt[0], shuffle=filt[1])
+            if kind == "array":
+                data = array_of(dt, tuple(shape), seed)
+                f.create_array(where, name, data)
+            elif kind == "earray":
+                shape = tuple(shape) or (3,)
+                data = array_of(dt, shape, seed)
+                node = f.create_earray(where, name, h.Atom(dt), (0,) + shape[1:], filters=filters,
+                                       chunkshape=tuple(chunk[:len(shape)]))
+                cut = shape[0] // 2
+                node.append(data[:cut])
+                node.append(data[cut:])
+            else:
+                rows = (shape or [2])[0]
+                tdt = np.dtype([("a_" + np.dtype(dt).name, dt), ("value", "f8"), ("vec", "i4", (2,))])
+                data = np.zeros(rows, dtype=tdt)
+                data[tdt.names[0]] = array_of(dt, (rows,), seed)
+                data["value"] = np.arange(rows) * 0.5
+                data["vec"] = np.arange(2 * rows).reshape(rows, 2)
+                node = f.create_table(where, name, tdt, filters=filters, chunkshape=(chunk[0],))
+                node.append(data)
+            want[path + "/" + name] = data
+
+        with h.open_file(fn, "w") as f:
+            for name, item in spec.items():
+                if isinstance(item, dict):
+                    g = f.create_group("/", name, "group " + name)
+                    for sub, subitem in item.items():
+                        add(f, g, "/" + name, sub, subitem)
+                else:
+                    add(f, "/", "", name, item)
+        audit(fn)
+        with h.open_file(fn) as f:
+            found = [p for p in want if p in f]
+            assert sorted(found) == sorted(want)
+            for path, data in want.items():
+                got = f.get_node(path).read()
+                assert same(got, data), (path, got.dtype, data.dtype)
+        os.remove(fn)
+
+    check()
+    assert counter[0] >= 20                                   # the property really ran
