@@ -521,7 +521,12 @@ class Group(Node):
     _v_title = property(lambda self: self._v_attrs.get("TITLE", ""))
 
     def _f_get_child(self, name):
-        return getattr(self, name)
+        """The child called ``name`` -- also when the name is not usable as an attribute
+        (``__dict__``, ``_v_attrs``, ...: PyTables' natural-naming caveat)."""
+        try:
+            return self._v_children[name]
+        except KeyError:
+            raise NoSuchNodeError("group %r does not have a child named %r" % (self._v_name, name))
 
     _f_getChild = _f_get_child
 
@@ -1216,12 +1221,16 @@ class File(object):
         for part in [p for p in str(where).split("/") if p]:
             if not isinstance(node, Group):
                 raise NoSuchNodeError(where)
-            node = getattr(node, part)
+            node = node._f_get_child(part)
         return node
 
     def get_node(self, where, name=None):
         node = self._where(where)
-        return node if name is None else getattr(node, name)
+        if name is None:
+            return node
+        if not isinstance(node, Group):
+            raise NoSuchNodeError("%r is not a group" % (where,))
+        return node._f_get_child(name)
 
     def list_nodes(self, where):
         return list(self._where(where))
