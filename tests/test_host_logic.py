@@ -316,6 +316,27 @@ def test_save_and_wrapper_model_roundtrip(tmp_path, ext):
             m.saveallresults(filename=str(tmp_path / "blosc.hf5"), hdf5complevel=2, hdf5complib="blosc")
 
 
+def test_default_results_file_name_and_type(tmp_path, monkeypatch):
+    """No file name: ``run<datetime>.hf5`` in the working directory (cosmomodels.py:239-242);
+    a background-only model goes to the ``bgresults`` group with a float64 yresult (:263-267, 346)."""
+    from pyflation_b200 import cosmomodels as c, hdf5lite
+    monkeypatch.chdir(tmp_path)
+    bg = c.CanonicalBackground(ystart=np.array([18.0, -0.1, 0.0]), tend=83.0, tstep_wanted=0.01,
+                               potential_func="msqphisq", pot_params={"nfields": 1}, nfields=1)
+    bg.tresult = np.arange(5) * 0.01
+    bg.yresult = np.arange(15.0).reshape(5, 3, 1)
+    bg.lastparams = bg.callingparams()
+    path = bg.saveallresults()
+    assert os.path.dirname(path) == str(tmp_path) and os.path.basename(path) == "run" + bg.lastparams["datetime"] + ".hf5"
+    with hdf5lite.open_file(path) as rf:
+        assert list(rf.root._v_children) == ["bgresults"]
+        res = rf.root.bgresults
+        assert res.yresult.dtype == np.float64 and np.array_equal(res.yresult.read(), bg.yresult)
+        assert res.parameters[0]["classname"] == b"CanonicalBackground" and res.parameters[0]["nfields"] == 1
+        assert [r["name"] for r in res.pot_params] == [b"nfields"]
+    assert c.CosmologicalModel.saveallresults(bg, filename=str(tmp_path / "x.npz")).endswith("x.npz")
+
+
 def test_committed_bench_record_has_contract_keys():
     """The bench line recorded for this round carries every key of the measurement contract."""
     import json
