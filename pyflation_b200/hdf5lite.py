@@ -157,8 +157,8 @@ def decode_datatype(buf, p=0):
         q += 12
     elif cls == 3:                                        # fixed-length string
         dt = np.dtype("S%d" % size)
-    elif cls == 4:                                        # bit field
-        dt = np.dtype("%su%d" % (order, size))
+    elif cls == 4:                                        # bit field; one byte = PyTables' bool (H5T_STD_B8)
+        dt = np.dtype(np.bool_) if size == 1 else np.dtype("%su%d" % (order, size))
         q += 4
     elif cls == 5:                                        # opaque
         q += _pad8(bits & 0xFF)
@@ -196,7 +196,7 @@ def decode_datatype(buf, p=0):
             dt = np.dtype("%sc%d" % (formats[0].byteorder.replace("=", "<").replace("|", "<"), size))
         else:
             dt = np.dtype(dict(names=names, formats=formats, offsets=offsets, itemsize=size))
-    elif cls == 8:                                        # enumeration (PyTables: bool)
+    elif cls == 8:                                        # enumeration (h5py's bool: FALSE / TRUE on int8)
         base, used = decode_datatype(buf, q)
         q += used
         nmemb = bits & 0xFFFF
@@ -245,9 +245,8 @@ def encode_datatype(dt):
         return struct.pack("<B3BI", 0x11, 0x20, 8 * size - 1, 0, size) + _float_props(size)
     if dt.kind in "iu":
         return struct.pack("<B3BI", 0x10, 0x08 if dt.kind == "i" else 0, 0, 0, size) + struct.pack("<HH", 0, 8 * size)
-    if dt.kind == "b":                                    # PyTables' bool: enum of int8 FALSE / TRUE
-        return (struct.pack("<B3BI", 0x18, 2, 0, 0, 1) + encode_datatype(np.int8)
-                + b"FALSE\0\0\0" + b"TRUE\0\0\0\0" + b"\0\1")
+    if dt.kind == "b":                                    # PyTables' bool: the 8-bit bit field H5T_STD_B8
+        return struct.pack("<B3BI", 0x14, 0, 0, 0, 1) + struct.pack("<HH", 0, 8)
     if dt.kind == "S":
         return struct.pack("<B3BI", 0x13, 0, 0, 0, max(size, 1))
     if dt.kind == "c":

@@ -198,6 +198,11 @@ def test_datatype_messages_round_trip_and_match_libhdf5_bytes():
         enc = h.encode_datatype(dt)
         back, used = h.decode_datatype(enc)
         assert used == len(enc) and back == np.dtype(dt), (dt, back)
+    # bool: PyTables' 8-bit bit field is what is written; h5py's FALSE / TRUE enum is read as well
+    assert h.encode_datatype(np.bool_) == struct.pack("<B3BIHH", 0x14, 0, 0, 0, 1, 0, 8)
+    h5py_bool = (struct.pack("<B3BI", 0x18, 2, 0, 0, 1) + h.encode_datatype(np.int8)
+                 + b"FALSE\0\0\0" + b"TRUE\0\0\0\0" + b"\0\1")
+    assert h.decode_datatype(h5py_bool) == (np.dtype(np.bool_), len(h5py_bool))
     # PyTables' complex: a compound of two doubles called r and i
     enc = h.encode_datatype(np.complex128)
     assert enc[0] == 0x16 and enc[4:8] == struct.pack("<I", 16) and enc[8:9] == b"r" and b"i\0" in enc
@@ -521,3 +526,34 @@ def test_random_trees_round_trip_and_pass_the_audit(tmp_path):
 
     check()
     assert counter[0] >= 20                                   # the property really ran
+
+
+def test_decoders_of_message_versions_the_writer_never_emits():
+    """Versions libhdf5 >= 1.8 may choose (dataspace v2, attribute v2 / v3, compound v3, array v3,
+    filter pipeline v2), hand-encoded from the specification."""
+    from pyflation_b200.hdf5lite import _decode_dataspace, _decode_attribute, _decode_filters
+    f8 = h.encode_datatype(np.float64)
+    # dataspace v2: version, rank, flags (max dims present), type (1 = simple), dims, max dims
+    ds2 = struct.pack("<BBBB", 2, 2, 1, 1) + struct.pack("<4Q", 3, 5, h.UNDEF, 5)
+    assert _decode_dataspace(ds2, 0) == ((3, 5), (None, 5))
+    assert _decode_dataspace(struct.pack("<BBBB", 2, 0, 0, 2), 0) == (None, None)        # null dataspace
+    assert _decode_dataspace(struct.pack("<BBBB", 2, 0, 0, 0), 0) == ((), ())            # scalar
+    # attribute v3: version, flags, name / datatype / dataspace sizes, character set; nothing padded
+    name, space = b"answer\0", struct.pack("<BBBB", 2, 1, 0, 1) + struct.pack("<Q", 2)
+    a3 = struct.pack("<BBHHHB", 3, 0, len(name), len(f8), len(space), 0) + name + f8 + space + \
+        np.array([1.5, -2.0]).tobytes()
+    got = _decode_attribute(a3, 0)
+    assert got[0] == "answer" and got[1].tolist() == [1.5, -2.0]
+    a2 = struct.pack("<BBHHH", 2, 0, len(name), len(f8), len(space)) + name + f8 + space + \
+        np.array([1.5, -2.0]).tobytes()
+    assert _decode_attribute(a2, 0)[1].tolist() == [1.5, -2.0]
+    # compound v3: names not padded, member offsets in the fewest bytes that hold the size (1 here)
+    i4 = h.encode_datatype(np.int32)
+    arr3 = struct.pack("<B3BI", 0x3A, 0, 0, 0, 24) + struct.pack("<B", 1) + struct.pack("<I", 3) + f8
+    c3 = (struct.pack("<B3BI", 0x36, 2, 0, 0, 28) + b"n\0" + b"\0" + i4 + b"vec\0" + b"\x04" + arr3)
+    dt, used = h.decode_datatype(c3)
+    assert used == len(c3) and dt == np.dtype([("n", "<i4"), ("vec", "<f8", (3,))])
+    # filter pipeline v2: no name for the predefined filters, nothing padded
+    p2 = struct.pack("<BB", 2, 2) + struct.pack("<HHH", 2, 1, 1) + struct.pack("<I", 8) + \
+        struct.pack("<HHH", 1, 1, 1) + struct.pack("<I", 4)
+    assert _decode_filters(p2, 0) == [(2, 1, (8,)), (1, 1, (4,))]
